@@ -1,0 +1,116 @@
+"""Checkpoint format of the reference + synthetic weights for offline work.
+
+Reference format (tools/train_utils/__init__.py:125-180): ``torch.save`` of
+``{'epoch','it','model_state','optimizer_state','version'}``; ``model_state``
+keys carry an optional ``module.`` prefix (saved through the DataParallel
+wrapper, tools/test.py:142-143) and are copied only where name and shape match.
+
+Parameter names: ``neck.backbone.{conv0,down0,...}.{0,3,6}.weight``
+in spconv-v1 layout ``[kz,ky,kx,Cin,Cout]`` with BatchNorm1d at ``.{1,4,7}``;
+``neck.fcn.conv{0..7}.weight`` / ``neck.fcn.bn{0..7}.*``; ``rpn_head.conv_{cls,box,
+dir_cls}.{weight,bias}``; ``extra_head.convs.{0,1,3}.*``.  The aux-head keys
+(``neck.point_fc/point_cls/point_reg``, cmn.py:27-29) are training-only and ignored.
+"""
+import math
+import os
+
+import torch
+
+# (name, Cin, Cout, kernel, expected active taps used to scale the synthetic init)
+_SPARSE_LAYERS = [
+    ("conv0.0", 4, 16, 3, 4.0), ("conv0.3", 16, 16, 3, 4.0),
+    ("down0.0", 16, 32, 3, 3.0),
+    ("conv1.0", 32, 32, 3, 8.0), ("conv1.3", 32, 32, 3, 8.0),
+    ("down1.0", 32, 64, 3, 5.0),
+    ("conv2.0", 64, 64, 3, 9.0), ("conv2.3", 64, 64, 3, 9.0), ("conv2.6", 64, 64, 3, 9.0),
+    ("down2.0", 64, 64, 3, 6.0),
+    ("conv3.0", 64, 64, 3, 14.0), ("conv3.3", 64, 64, 3, 14.0), ("conv3.6", 64, 64, 3, 14.0),
+    ("extra_conv.0", 64, 64, 1, 1.0),
+]
+
+
+def _bn(sd, prefix, c, g):
+    sd[prefix + ".weight"] = torch.rand(c, generator=g) * 0.5 + 0.75
+    sd[prefix + ".bias"] = torch.randn(c, generator=g) * 0.1
+    sd[prefix + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+    sd[prefix + ".running_var"] = torch.rand(c, generator=g) + 0.5
+
+
+def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, num_parts=28,
+                              cls_gain=1.0, cls_bias=-5.0):
+    """Random-but-fixed weights in the reference's state_dict naming.
+
+    No checkpoint is reachable offline, so benchmarks and parity tests use these.
+    Scales follow a He-style rule on the *expected active* fan-in so activations
+    stay O(1) through the 13 sparse + 8 dense layers; BatchNorm statistics are
+    randomised so BN is not an identity.  ``cls_gain``/``cls_bias``
+    shape the RPN class logits so that, like a trained detector, only a few
+    hundred anchors per frame pass the 0.1 guided-anchor threshold
+    (constants picked by tests/tools/calibrate_synthetic_weights.py).
+    """
+    g = torch.Generator().manual_seed(int(seed))
+    sd = {}
+    p = "neck.backbone."
+    for name, cin, cout, k, taps in _SPARSE_LAYERS:
+        std = math.sqrt(2.0 / (cin * taps))
+        sd[p + name + ".weight"] = torch.randn(k, k, k, cin, cout, generator=g) * std
+        blk, idx = name.split(".")
+        _bn(sd, "%s%s.%d" % (p, blk, int(idx) + 1), cout, g)
+    p = "neck.fcn."
+    for i in range(8):
+        cin = bev_in if i == 0 else num_filters
+        k = 1 if i == 7 else 3
+        eff = cin * k * k * (0.06 if i == 0 else 1.0)   # conv0 sees a ~4-6 % occupied map
+        sd["%sconv%d.weight" % (p, i)] = torch.randn(num_filters, cin, k, k, generator=g) * math.sqrt(2.0 / eff)
+        _bn(sd, "%sbn%d" % (p, i), num_filters, g)
+    p = "rpn_head."
+    na = 2 * num_class
+    s = math.sqrt(1.0 / num_filters)
+    sd[p + "conv_cls.weight"] = torch.randn(na * num_class, num_filters, 1, 1, generator=g) * s * cls_gain
+    sd[p + "conv_cls.bias"] = torch.randn(na * num_class, generator=g) * 0.05 + cls_bias
+    sd[p + "conv_box.weight"] = torch.randn(na * 7, num_filters, 1, 1, generator=g) * s * 0.15
+    sd[p + "conv_box.bias"] = torch.randn(na * 7, generator=g) * 0.02
+    sd[p + "conv_dir_cls.weight"] = torch.randn(na * 2, num_filters, 1, 1, generator=g) * s
+    sd[p + "conv_dir_cls.bias"] = torch.randn(na * 2, generator=g) * 0.05
+    p = "extra_head."
+    sd[p + "convs.0.weight"] = torch.randn(num_parts, num_filters, 3, 3, generator=g) * math.sqrt(2.0 / (num_filters * 9))
+    _bn(sd, p + "convs.1", num_parts, g)
+    sd[p + "convs.3.weight"] = torch.randn(num_parts, num_parts, 1, 1, generator=g) * math.sqrt(2.0 / num_parts)
+    return sd
+
+
+def save_checkpoint(state_dict, filename, epoch=0, it=0, module_prefix=False):
+    """Write the reference's checkpoint dict (train_utils/__init__.py:125-152)."""
+    ms = {("module." + k if module_prefix else k): v for k, v in state_dict.items()}
+    torch.save({"epoch": epoch, "it": it, "model_state": ms, "optimizer_state": None,
+                "version": "sassd_b200"}, filename)
+
+
+def load_params_from_file(model, filename, to_cpu=False, verbose=False):
+    """Mirror of tools/train_utils/__init__.py:154-180: copy every key whose name
+    (after stripping an optional ``module.`` prefix) and shape match; report the
+    rest.  Returns (n_loaded, missing_keys)."""
+    if not os.path.isfile(filename):
+        raise FileNotFoundError(filename)
+    ckpt = torch.load(filename, map_location="cpu" if to_cpu else None, weights_only=False)
+    disk = ckpt["model_state"] if isinstance(ckpt, dict) and "model_state" in ckpt else ckpt
+    return load_state_dict_into(model, disk, verbose=verbose)
+
+
+def load_state_dict_into(model, disk, verbose=False):
+    own = model.state_dict()
+    update = {}
+    for key, val in disk.items():
+        k = key[7:] if key.startswith("module.") else key
+        if k in own and tuple(own[k].shape) == tuple(val.shape):
+            update[k] = val
+    own.update(update)
+    model.load_state_dict(own)
+    missing = [k for k in own if k not in update]
+    if verbose:
+        for k in missing:
+            print("Not updated weight %s: %s" % (k, str(tuple(own[k].shape))))
+        print("==> Done (loaded %d/%d)" % (len(update), len(own)))
+    if hasattr(model, "refresh_packed_weights"):
+        model.refresh_packed_weights()
+    return len(update), missing
