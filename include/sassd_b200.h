@@ -1,0 +1,209 @@
+/* sassd_b200 — C ABI of the B200-native SA-SSD inference hot path.
+ *
+ * Drop-in boundary: these are the entry
+ * points a binding of the reference's native extensions for this path would
+ * call.  Plain C: device pointers, sizes, a CUDA stream; no torch types.
+ *
+ * Conventions (differences from the reference ABI are deliberate and listed):
+ *  - every pointer is a DEVICE pointer unless the name says host_;
+ *  - every function takes the stream to launch on (the reference launches on
+ *    the legacy default stream, iou3d_kernel.cu:359-386) and returns an int
+ *    status (SASSD_OK or a negative SASSD_ERR_*); nothing exits the process
+ *    (the reference calls exit(), iou3d.cpp:13-21) and nothing is allocated or
+ *    freed inside a call (the reference cudaMalloc/cudaFree's per NMS call,
+ *    iou3d.cpp:87,98) — scratch comes in through `ws` with a *_workspace_bytes query;
+ *  - data-dependent sizes (voxel counts, active rows, guided anchors, kept boxes)
+ *    live in device memory (`d_*` int32 counters) so that a whole frame runs
+ *    without a host round trip and can be captured in a CUDA graph; buffers are
+ *    sized by capacity (`*_cap`).  A capacity overflow truncates the output and
+ *    sets a bit in the int32 word `d_status` (SASSD_FLAG_*).
+ *  - layouts: points [N,4] f32 (x,y,z,r); voxel coordinates int32 (b,z,y,x);
+ *    boxes [x,y,z(bottom),w,l,h,ry]; BEV boxes [x1,y1,x2,y2,ry];
+ *    feature matrices row-major [rows, channels]; dense maps NHWC.
+ */
+#ifndef SASSD_B200_H
+#define SASSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sassd_stream_t; /* cudaStream_t */
+
+enum {
+    SASSD_OK = 0,
+    SASSD_ERR_ARG = -1,       /* bad argument (null pointer, unsupported size) */
+    SASSD_ERR_LAUNCH = -2,    /* CUDA reported a launch error */
+    SASSD_ERR_WORKSPACE = -3, /* workspace too small */
+    SASSD_ERR_UNSUPPORTED = -4
+};
+
+enum { /* bits of *d_status */
+    SASSD_FLAG_VOXEL_CAP = 1,   /* more voxel rows than the output capacity */
+    SASSD_FLAG_ROWS_CAP = 2,    /* strided-conv output rows exceed capacity */
+    SASSD_FLAG_GUIDED_CAP = 4,  /* guided anchors per frame exceed capacity */
+    SASSD_FLAG_NMS_CAP = 8,     /* NMS candidates per frame exceed capacity */
+    SASSD_FLAG_HASH_FULL = 16
+};
+
+int sassd_version(void);
+
+/* ------------------------------------------------------------------------
+ * Voxelization.  Replaces mmdet/ops/points_op/points_ops.py:104-164
+ * (points_to_voxel, reverse_index=True) called from
+ * mmdet/core/point_cloud/voxel_generator.py:22-25, fused with
+ * SingleStageDetector.merge_second_batch's batch-index padding
+ * (mmdet/models/detectors/single_stage.py:57-65) and SimpleVoxel.forward
+ * (mmdet/models/backbones/vxnet.py:110-116).
+ *
+ * points: frames concatenated, frame b = rows [pt_off[b], pt_off[b+1]).
+ * Outputs are bit-identical to the sequential reference per frame (first-touch
+ * voxel order, first `max_points` points, stop at voxel `max_voxels`), rows of
+ * frame b start at sum of the previous frames' counts:
+ *   voxels [rows_cap, max_points, 4] (zero padded), coors [rows_cap,4] (b,z,y,x),
+ *   num_points [rows_cap], mean [rows_cap,4] (may be NULL),
+ *   d_frame_rows [batch+1] = exclusive row offsets, last = total rows.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    float voxel_size[3];  /* x, y, z */
+    float range_min[3];   /* x, y, z */
+    int32_t grid[3];      /* x, y, z cells (1408, 1600, 40 under car_cfg) */
+    int32_t max_points;   /* <= 8 */
+    int32_t max_voxels;
+} sassd_voxel_params;
+
+size_t sassd_voxelize_workspace_bytes(int n_points_cap, int batch, int slots_per_frame);
+int sassd_voxelize(const float* points, const int32_t* d_pt_off, int n_points_cap, int batch,
+                   const sassd_voxel_params* host_params, int slots_per_frame,
+                   float* voxels, int32_t* coors, int32_t* num_points, float* mean, int rows_cap,
+                   int32_t* d_frame_rows, int32_t* d_status, void* ws, size_t ws_bytes, sassd_stream_t stream);
+
+/* SimpleVoxel.forward alone (vxnet.py:110-116): mean[r,:] = sum_s voxels[r,s,:4] / num_points[r]. */
+int sassd_voxel_mean(const float* voxels, const int32_t* num_points, const int32_t* d_rows, int rows_cap,
+                     int max_points, float* mean, sassd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * anchors_mask.  Replaces mmdet/datasets/kitti.py:333-343 +
+ * mmdet/core/bbox3d/geometry.py:675-709 (occupancy count, two cumsums,
+ * integral-image lookup, `> threshold`).  rects [n_anchors,4] int32 are the
+ * clamped cell indices (c0,c1,c2,c3) of each anchor's near-axis-aligned
+ * footprint — static, computed once on the host with the reference's fp32
+ * arithmetic.  mask [batch, n_anchors] uint8.
+ * ---------------------------------------------------------------------- */
+size_t sassd_anchor_mask_workspace_bytes(int batch, int H, int W);
+int sassd_anchor_mask(const int32_t* coors, const int32_t* d_rows, int rows_cap, int batch, int H, int W,
+                      const int32_t* rects, int n_anchors, int threshold, uint8_t* mask,
+                      void* ws, size_t ws_bytes, sassd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Rulebooks.  Replace spconv v1.0 `get_indice_pairs` (third-party; call sites
+ * mmdet/models/necks/cmn.py:139-173,197-212).  The hot path uses a neighbour
+ * table nbr[n_out, 27] (input row feeding output row o through kernel offset
+ * k = (kz*3+ky)*3+kx, -1 = none); sassd_rulebook_pairs re-indexes it into the
+ * spconv-v1 tables indice_pairs[2,27,n_cap] / indice_pair_num[27] (canonical
+ * order: per offset ascending output row).
+ * ---------------------------------------------------------------------- */
+/* hash index over active coordinates: keys/vals [slots] int32, slots a power of two >= 2*n_cap. */
+int sassd_hash_build(const int32_t* coors, const int32_t* d_rows, int rows_cap, int batch, int D, int H, int W,
+                     int32_t* keys, int32_t* vals, int slots, int32_t* d_status, sassd_stream_t stream);
+/* submanifold 3x3x3: output sites == input sites. */
+int sassd_rulebook_subm(const int32_t* coors, const int32_t* d_rows, int rows_cap, int D, int H, int W,
+                        const int32_t* keys, const int32_t* vals, int slots, int32_t* nbr, sassd_stream_t stream);
+/* strided conv (k=3,s=2,p=1): active output set, sorted by flattened (b,z,y,x). */
+size_t sassd_rulebook_conv_workspace_bytes(int batch, int Do, int Ho, int Wo);
+int sassd_rulebook_conv_outputs(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in, int batch,
+                                int D, int H, int W, int32_t* coors_out, int32_t* d_rows_out, int rows_cap_out,
+                                int32_t* d_status, void* ws, size_t ws_bytes, sassd_stream_t stream);
+/* neighbour table of the strided conv: nbr[o][k] = row of input cell 2*o - 1 + k. */
+int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* d_rows_out, int rows_cap_out, int D, int H, int W,
+                            const int32_t* keys_in, const int32_t* vals_in, int slots_in, int32_t* nbr,
+                            sassd_stream_t stream);
+int sassd_rulebook_pairs(const int32_t* nbr, const int32_t* d_rows_out, int rows_cap, int32_t* indice_pairs,
+                         int32_t* indice_pair_num, sassd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Gathered implicit-GEMM convolution — one kernel family for
+ *   SubMConv3d / SparseConv3d  (spconv v1.0 indice_conv; cmn.py:145-173,192-231)
+ *   SparseConv3d 1x1x1         (cmn.py:208-212)
+ *   nn.Conv2d 3x3 / 1x1 + BatchNorm2d(eval) + ReLU (BEVNet cmn.py:233-282,
+ *     SSDRotateHead ssd_rotate_head.py:120-125,218-231, PSWarpHead.convs :424-429)
+ *   out[m, :] = act( (sum_t in[row(m,t), :] @ W[t]) * scale + shift )
+ * mode TABLE : row(m,t) = nbr[m*taps + t]            (sparse layers)
+ * mode CONV2D: rows are pixels of a [batch,H,W] NHWC map, taps = 3x3 window, zero padding
+ * mode ROWS  : taps == 1, row(m,0) = m                (1x1 convs / plain GEMM)
+ * weight [taps, Cin, Cout] f32; scale/shift [Cout] (folded BatchNorm or bias); Cin % 4 == 0.
+ * precision: SASSD_PREC_FP32 = CUDA-core FFMA; SASSD_PREC_TF32X3 = tcgen05 3xTF32 split.
+ * ---------------------------------------------------------------------- */
+enum { SASSD_GCONV_TABLE = 0, SASSD_GCONV_CONV2D = 1, SASSD_GCONV_ROWS = 2 };
+enum { SASSD_PREC_FP32 = 0, SASSD_PREC_TF32X3 = 1 };
+typedef struct {
+    int32_t mode, precision;
+    int32_t cin, cout, taps;
+    int32_t in_stride, out_stride; /* floats per row */
+    int32_t rows_cap;              /* upper bound of rows (grid sizing) */
+    int32_t batch, H, W;           /* CONV2D only */
+    int32_t relu;
+} sassd_gconv_desc;
+int sassd_gconv(const sassd_gconv_desc* host_desc, const float* in, const float* weight, const float* scale,
+                const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, sassd_stream_t stream);
+
+/* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
+ * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;
+ * the permutation is folded into the first BEV conv's weights).  The map must be
+ * zeroed by the caller (cudaMemsetAsync). */
+int sassd_sparse_to_bev(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
+                        int D, int H, int W, float* bev, sassd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * second_box_decode + get_guided_anchors (ssd_rotate_head.py:53-91,307-372):
+ * head [batch,H,W,head_stride] NHWC holds conv_box | conv_cls | conv_dir_cls
+ * channels back to back; anchors [n_anchors,7] in (class,y,x,rot) order;
+ * mask [batch,n_anchors] uint8.  Per frame, in anchor order: keep mask &&
+ * max_c sigmoid(cls) > thr, decode, flip direction.  Outputs (capacity k_cap per frame):
+ * boxes [batch,k_cap,7], labels [batch,k_cap] i32, index [batch,k_cap] i32
+ * (anchor id), d_k [batch].
+ * ---------------------------------------------------------------------- */
+size_t sassd_decode_select_workspace_bytes(int batch, int n_anchors);
+int sassd_decode_select(const float* head, int head_stride, int batch, int H, int W, int num_class,
+                        const float* anchors, const uint8_t* mask, int n_anchors, float thr,
+                        float* boxes, int32_t* labels, int32_t* index, int32_t* d_k, int k_cap,
+                        int32_t* d_status, void* ws, size_t ws_bytes, sassd_stream_t stream);
+
+/* PSWarpHead sampling (ssd_rotate_head.py:374-414,431-447): feat [batch,H,W,feat_stride]
+ * NHWC with >= num_parts channels; part p = i*7+j samples channel p bilinearly at
+ * the (i,j) tap of the 4x7 window of each guided box; score = mean over parts (logit). */
+int sassd_pswarp(const float* feat, int feat_stride, int batch, int H, int W, const float* boxes,
+                 const int32_t* d_k, int k_cap, float off_x, float off_y, float spatial_scale,
+                 float* scores, sassd_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * get_rescore_bboxes (ssd_rotate_head.py:487-533) = sigmoid(score) > score_thr,
+ * boxes3d_to_bev_torch (iou3d_utils.py:47-60), nms_gpu (iou3d_utils.py:114-128,
+ * iou3d.cpp:73-120, iou3d_kernel.cu:250-292) with the greedy sweep on the
+ * device, gather.  Sort is stable (score descending, then candidate order).
+ * det [batch,det_cap,9] = (x,y,z,w,l,h,ry,score,label); d_ndet [batch].
+ * ---------------------------------------------------------------------- */
+size_t sassd_rescore_nms_workspace_bytes(int batch, int k_cap, int nms_cap);
+int sassd_rescore_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* d_k,
+                      int batch, int k_cap, float score_thr, float iou_thr, int nms_cap,
+                      float* det, int32_t* d_ndet, int det_cap, int32_t* d_status,
+                      void* ws, size_t ws_bytes, sassd_stream_t stream);
+
+/* iou3d_cuda.nms_gpu alone (iou3d.cpp:73-120): boxes [n,5] already sorted by
+ * score; mask [n, ceil(n/64)] u64 in the reference layout (only columns j > i
+ * are filled; the reference also fills the unused lower triangle); keep [n]
+ * int64 indices, *d_nkeep their number. */
+size_t sassd_nms_workspace_bytes(int n);
+int sassd_nms_mask(const float* boxes5, int n, float thr, uint64_t* mask, sassd_stream_t stream);
+int sassd_nms_sorted(const float* boxes5, int n, float thr, int64_t* keep, int32_t* d_nkeep,
+                     void* ws, size_t ws_bytes, sassd_stream_t stream);
+/* iou3d_cuda.boxes_iou_bev_gpu (iou3d.cpp:52-71): dense [na, nb] rotated BEV IoU. */
+int sassd_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou, sassd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SASSD_B200_H */

@@ -36,14 +36,18 @@ def _bn(sd, prefix, c, g):
     sd[prefix + ".running_var"] = torch.rand(c, generator=g) + 0.5
 
 
+_CALIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth_calib.npz")
+
+
 def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, num_parts=28,
-                              cls_gain=1.0, cls_bias=-5.0):
+                              cls_gain=2.0, cls_bias=-5.0, calibrated=True):
     """Random-but-fixed weights in the reference's state_dict naming.
 
     No checkpoint is reachable offline, so benchmarks and parity tests use these.
     Scales follow a He-style rule on the *expected active* fan-in so activations
-    stay O(1) through the 13 sparse + 8 dense layers; BatchNorm statistics are
-    randomised so BN is not an identity.  ``cls_gain``/``cls_bias``
+    stay O(1) through the 13 sparse + 8 dense layers; BatchNorm affine parameters are
+    randomised and, for seed 0, the running statistics come from a calibration pass over
+    synthetic frames (synth_calib.npz) so that BN is neither an identity nor a blow-up.  ``cls_gain``/``cls_bias``
     shape the RPN class logits so that, like a trained detector, only a few
     hundred anchors per frame pass the 0.1 guided-anchor threshold
     (constants picked by tests/tools/calibrate_synthetic_weights.py).
@@ -76,6 +80,13 @@ def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, 
     sd[p + "convs.0.weight"] = torch.randn(num_parts, num_filters, 3, 3, generator=g) * math.sqrt(2.0 / (num_filters * 9))
     _bn(sd, p + "convs.1", num_parts, g)
     sd[p + "convs.3.weight"] = torch.randn(num_parts, num_parts, 1, 1, generator=g) * math.sqrt(2.0 / num_parts)
+    if calibrated and seed == 0 and num_filters == 256 and bev_in == 320 and os.path.isfile(_CALIB):
+        # BatchNorm running statistics as training-mode BN would have recorded them on synthetic
+        # frames (tests/tools/calibrate_synthetic_weights.py): keeps activations O(1) in all 22 layers
+        import numpy as np
+        with np.load(_CALIB) as z:
+            for k in z.files:
+                sd[k] = torch.from_numpy(z[k].copy())
     return sd
 
 

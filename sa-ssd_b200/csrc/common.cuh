@@ -1,0 +1,84 @@
+// Shared helpers for the sassd_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sassd_b200.h"
+
+#define SASSD_EMPTY_KEY (-1)
+
+// Launch-error -> status code (the C ABI never exits or throws).
+static inline int sassd_check_launch() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SASSD_OK : SASSD_ERR_LAUNCH;
+}
+
+static inline int sassd_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Persistent-style grid sizing: enough CTAs to cover `work` items, capped at
+// `waves` resident waves of the 148-SM part (grid-stride loops pick up the rest).
+static inline int sassd_grid(long long work, int block, int ctas_per_sm = 8) {
+    long long need = (work + block - 1) / block;
+    long long cap = 148LL * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ uint32_t sassd_hash32(uint32_t k) {
+    // Fibonacci hashing followed by a xor-fold; table sizes are powers of two.
+    k *= 0x9E3779B1u;
+    k ^= k >> 15;
+    return k;
+}
+
+// Open-addressing insert of a unique key; returns the slot.  keys[] must be
+// pre-filled with SASSD_EMPTY_KEY.  `mask` = slots - 1.
+__device__ __forceinline__ int sassd_hash_insert_unique(int* __restrict__ keys, uint32_t mask, int key) {
+    uint32_t s = sassd_hash32((uint32_t)key) & mask;
+    while (true) {
+        int prev = atomicCAS(&keys[s], SASSD_EMPTY_KEY, key);
+        if (prev == SASSD_EMPTY_KEY || prev == key) return (int)s;
+        s = (s + 1) & mask;
+    }
+}
+
+// Read-only lookup; returns slot or -1.
+__device__ __forceinline__ int sassd_hash_find(const int* __restrict__ keys, uint32_t mask, int key) {
+    uint32_t s = sassd_hash32((uint32_t)key) & mask;
+    while (true) {
+        int k = __ldg(&keys[s]);
+        if (k == key) return (int)s;
+        if (k == SASSD_EMPTY_KEY) return -1;
+        s = (s + 1) & mask;
+    }
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// Returns the exclusive prefix; *total receives the block sum.  `smem` needs 33 ints.
+__device__ __forceinline__ int sassd_block_exscan(int v, int* smem, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarp ? smem[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        smem[lane] = winc - w;           // exclusive warp offsets
+        if (lane == 31) smem[32] = winc; // block total
+    }
+    __syncthreads();
+    int res = smem[warp] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}

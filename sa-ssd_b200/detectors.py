@@ -1,0 +1,162 @@
+"""``mmdet.models.detectors`` mirror for the hot path: SingleStageDetector
+(mmdet/models/detectors/single_stage.py:13-41,52-73,110-131; base.py:77-81).
+
+Two entry points:
+  * ``forward(img, img_meta, return_loss=False, **kwargs)`` / ``forward_test`` — the
+    reference's call signature (tools/test.py:31) with pre-voxelized inputs produced by
+    the dataset side (kitti.py:296-352);
+  * ``forward_points(points)`` — the fused path from raw Velodyne points on the host:
+    one H2D copy, voxelize + anchors_mask + backbone + neck + heads + PSWarp + NMS with
+    every data-dependent size kept on the device, one D2H copy of the fixed-size result.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import builder, ops
+from .single_stage_heads import unpack_detections
+
+
+class SingleStageDetector(nn.Module):
+    def __init__(self, backbone, neck=None, bbox_head=None, extra_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None):
+        super().__init__()
+        self.backbone = builder.build_backbone(backbone)
+        if neck is None:
+            raise NotImplementedError
+        self.neck = builder.build_neck(neck)
+        if bbox_head is not None:
+            self.rpn_head = builder.build_single_stage_head(bbox_head)
+        if extra_head is not None:
+            self.extra_head = builder.build_single_stage_head(extra_head)
+        self.train_cfg = train_cfg
+        self.test_cfg = test_cfg
+        self.class_names = None          # set by the caller, tools/test.py:139
+        self.guided_thr = 0.1            # hard-coded in the reference, single_stage.py:122
+        self.voxel_generator = None      # fused path: attach_data_pipeline()
+        self.anchor_set = None
+        self._pinned = None
+        if isinstance(pretrained, str):
+            from .checkpoint import load_params_from_file
+            load_params_from_file(self, pretrained)
+        self.eval()
+
+    @property
+    def with_rpn(self):
+        return hasattr(self, "rpn_head") and self.rpn_head is not None
+
+    def set_precision(self, precision):
+        self.neck.set_precision(precision)
+        self.rpn_head.precision = precision
+        self.extra_head.precision = precision
+
+    def refresh_packed_weights(self):
+        pass  # packed/folded tensors are version-checked on use
+
+    # ------------------------------------------------------------------ reference-signature path
+    def merge_second_batch(self, batch_args):
+        """single_stage.py:52-73 (torch.cat / F.pad are data movement only)."""
+        ret = {}
+        for key, elems in batch_args.items():
+            if key in ("voxels", "num_points"):
+                ret[key] = torch.cat(elems, dim=0)
+            elif key == "coordinates":
+                ret[key] = torch.cat([F.pad(c, [1, 0, 0, 0], mode="constant", value=i)
+                                      for i, c in enumerate(elems)], dim=0)
+            elif key in ("img_meta", "gt_labels", "gt_bboxes", "gt_types"):
+                ret[key] = elems
+            elif isinstance(elems, dict):
+                ret[key] = {k: torch.stack(v, dim=0) for k, v in elems.items()}
+            else:
+                ret[key] = torch.stack(elems, dim=0)
+        return ret
+
+    def forward(self, img=None, img_meta=None, return_loss=False, **kwargs):
+        if return_loss:
+            raise NotImplementedError("training (forward_train, single_stage.py:75-108) is out of scope")
+        return self.forward_test(img, img_meta, **kwargs)
+
+    def forward_test(self, img, img_meta, **kwargs):
+        """single_stage.py:110-131.  Returns, per frame, a dict(boxes_lidar [D,7], scores [D],
+        label_preds [D]) — the inputs of kitti_bbox2results (transforms.py:225-279), which needs
+        the KITTI calibration and is the next row of the port."""
+        ops.require_cuda()
+        batch_size = len(img_meta)
+        dev = next(self.parameters()).device
+        ret = self.merge_second_batch({k: v for k, v in kwargs.items() if v is not None and k not in
+                                       ("gt_labels", "gt_bboxes", "gt_types")})
+        voxels = ret["voxels"].to(dev).float().contiguous()
+        num_points = ret["num_points"].to(dev)
+        coords = ret["coordinates"].to(dev).int().contiguous()
+        vx = self.backbone(voxels, num_points)
+        x, conv6 = self.neck(vx, coords, batch_size, is_test=True)
+        rpn_outs = self.rpn_head.forward(x)
+        guided_anchors, anchor_labels = self.rpn_head.get_guided_anchors(
+            *rpn_outs, ret["anchors"].to(dev), ret["anchors_mask"].to(dev), None, None, thr=self.guided_thr)
+        bbox_score = self.extra_head(conv6, guided_anchors, is_test=True)
+        det_bboxes, det_scores, det_labels = self.extra_head.get_rescore_bboxes(
+            guided_anchors, bbox_score, anchor_labels, img_meta, self.test_cfg.extra)
+        return [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(det_bboxes, det_scores, det_labels)]
+
+    # ------------------------------------------------------------------ fused raw-points path
+    def attach_data_pipeline(self, voxel_generator, anchor_set):
+        """Give the detector the data-side objects of the config (cfg.data.val.generator /
+        anchor_generator) so that raw points are the only per-frame input."""
+        self.voxel_generator = voxel_generator
+        dev = next(self.parameters()).device
+        self.anchor_set = anchor_set.to(dev)
+        return self
+
+    def forward_device(self, points, pt_off, batch, max_points_per_frame):
+        """Everything on the device, no synchronisation.  points [Ncap,4], pt_off [batch+1] int32.
+        Returns (det [B,det_cap,9], d_ndet [B], status [1], aux dict)."""
+        dev = points.device
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        vg, aset = self.voxel_generator, self.anchor_set
+        voxels, coors, num, mean, frame_rows = vg.generate_device(points, pt_off, batch, max_points_per_frame, status)
+        d_rows = frame_rows[batch:batch + 1]
+        mask = aset.mask_device(coors, d_rows, batch)
+        y, conv6, xs = self.neck.forward_nhwc(mean, coors, batch, d_rows=d_rows, status=status)
+        head = self.rpn_head.forward_nhwc(y)
+        anchors, _ = aset.device_tensors()
+        boxes, labels, index, d_k = self.rpn_head.guided_anchors_device(head, anchors, mask, self.guided_thr, status)
+        scores = self.extra_head.forward_device(conv6, boxes, d_k)
+        det, d_ndet = self.extra_head.rescore_device(boxes, scores, labels, d_k, self.test_cfg.extra, status)
+        aux = dict(voxels=voxels, coors=coors, num_points=num, mean=mean, frame_rows=frame_rows, mask=mask, x=y,
+                   conv6=conv6, head=head, guided=boxes, guided_labels=labels, guided_index=index, d_k=d_k,
+                   ps_scores=scores, sparse=xs)
+        return det, d_ndet, status, aux
+
+    def stage_points(self, points_list):
+        """Host side of the fused path: concatenate the frames into one pinned buffer."""
+        counts = [int(p.shape[0]) for p in points_list]
+        total = sum(counts)
+        need = max(total, 1)
+        if self._pinned is None or self._pinned[0].shape[0] < need or self._pinned[1].shape[0] < len(counts) + 1:
+            self._pinned = (torch.empty((max(need, 1 << 16), 4), dtype=torch.float32).pin_memory(),
+                            torch.empty((max(len(counts) + 1, 65),), dtype=torch.int32).pin_memory())
+        hp, ho = self._pinned
+        o = 0
+        ho[0] = 0
+        for i, p in enumerate(points_list):
+            n = counts[i]
+            hp[o:o + n] = torch.from_numpy(np.ascontiguousarray(p[:, :4], dtype=np.float32)) if n else hp[o:o]
+            o += n
+            ho[i + 1] = o
+        return hp[:need], ho[:len(counts) + 1], counts
+
+    def forward_points(self, points_list, return_aux=False):
+        """Raw points in (list of [N_i,>=4] numpy arrays), detections out: per frame a dict of
+        boxes_lidar [D,7], scores [D], label_preds [D] (or None entries when nothing survives)."""
+        ops.require_cuda()
+        if self.voxel_generator is None or self.anchor_set is None:
+            raise RuntimeError("call attach_data_pipeline(voxel_generator, anchor_set) first")
+        dev = next(self.parameters()).device
+        hp, ho, counts = self.stage_points(points_list)
+        points = hp.to(dev, non_blocking=True)
+        pt_off = ho.to(dev, non_blocking=True)
+        det, d_ndet, status, aux = self.forward_device(points, pt_off, len(points_list), max(counts + [1]))
+        bbs, scs, lbs = unpack_detections(det, d_ndet, status)
+        out = [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(bbs, scs, lbs)]
+        return (out, aux) if return_aux else out

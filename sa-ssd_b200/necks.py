@@ -1,0 +1,195 @@
+"""``mmdet.models.necks`` mirror for the hot path: SpMiddleFHD = VxNet (sparse 3-D
+backbone) + BEVNet (dense BEV convs) — mmdet/models/necks/cmn.py:12-29,102-119,138-282.
+
+Parameter names and shapes equal the reference's so that its
+checkpoints load; all arithmetic runs in the sm_100a kernels of csrc/gconv.cu
+(BatchNorm folded into each conv's epilogue, eval mode).  The training-only aux head
+(cmn.py:44-100,121-135) is out of scope: its Linear parameters exist for checkpoint
+compatibility, ``is_test=False`` raises.
+"""
+import torch
+from torch import nn
+
+from . import ops, spconv
+from .spconv import fold_bn, _versions
+
+
+def single_conv(in_channels, out_channels, indice_key=None):
+    return spconv.SparseSequential(
+        spconv.SubMConv3d(in_channels, out_channels, 1, bias=False, indice_key=indice_key),
+        nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01),
+        nn.ReLU(),
+    )
+
+
+def _subm_block(n, in_channels, out_channels, indice_key):
+    layers = []
+    for i in range(n):
+        layers += [spconv.SubMConv3d(in_channels if i == 0 else out_channels, out_channels, 3, bias=False,
+                                     indice_key=indice_key),
+                   nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01), nn.ReLU()]
+    return spconv.SparseSequential(*layers)
+
+
+def double_conv(in_channels, out_channels, indice_key=None):
+    return _subm_block(2, in_channels, out_channels, indice_key)
+
+
+def triple_conv(in_channels, out_channels, indice_key=None):
+    return _subm_block(3, in_channels, out_channels, indice_key)
+
+
+def stride_conv(in_channels, out_channels, indice_key=None):
+    return spconv.SparseSequential(
+        spconv.SparseConv3d(in_channels, out_channels, 3, (2, 2, 2), padding=1, bias=False, indice_key=indice_key),
+        nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01),
+        nn.ReLU(),
+    )
+
+
+class VxNet(nn.Module):
+    """cmn.py:192-231."""
+
+    def __init__(self, num_input_features):
+        super().__init__()
+        self.conv0 = double_conv(num_input_features, 16, "subm0")
+        self.down0 = stride_conv(16, 32, "down0")
+        self.conv1 = double_conv(32, 32, "subm1")
+        self.down1 = stride_conv(32, 64, "down1")
+        self.conv2 = triple_conv(64, 64, "subm2")
+        self.down2 = stride_conv(64, 64, "down2")
+        self.conv3 = triple_conv(64, 64, "subm3")
+        self.extra_conv = spconv.SparseSequential(
+            spconv.SparseConv3d(64, 64, (1, 1, 1), (1, 1, 1), bias=False),
+            nn.BatchNorm1d(64, eps=1e-3, momentum=0.01),
+            nn.ReLU(),
+        )
+
+    def forward(self, x):
+        middle = []
+        x = self.conv0(x)
+        x = self.down0(x)
+        x = self.conv1(x)
+        middle.append(x)
+        x = self.down1(x)
+        x = self.conv2(x)
+        middle.append(x)
+        x = self.down2(x)
+        x = self.conv3(x)
+        middle.append(x)
+        out = self.extra_conv(x)
+        return out, middle
+
+    def set_precision(self, precision):
+        for m in self.modules():
+            if isinstance(m, spconv._SparseConvBase):
+                m.precision = precision
+
+
+def pack_conv2d_weight(w, dc_order=None):
+    """[Cout, Cin, kh, kw] -> [taps, Cin, Cout] (tap = ky*3+kx).  ``dc_order=(C, D)`` re-orders
+    the input channels from the reference's dense() order c*D+d to the internal d*C+c."""
+    cout, cin, kh, kw = w.shape
+    p = w.detach().permute(2, 3, 1, 0).reshape(kh * kw, cin, cout)
+    if dc_order is not None:
+        C, D = dc_order
+        p = p.reshape(kh * kw, C, D, cout).permute(0, 2, 1, 3).reshape(kh * kw, cin, cout)
+    return p.contiguous().float()
+
+
+def conv2d_nhwc(x, weight_packed, scale, shift, relu, cout, precision=ops.PREC_FP32, out=None):
+    """x [B,H,W,Cin] NHWC contiguous -> [B,H,W,cout_stride]; 3x3 (pad 1) when taps == 9, 1x1 when 1."""
+    B, H, W, cin = x.shape
+    taps = weight_packed.shape[0]
+    stride = (cout + 3) // 4 * 4
+    if out is None:
+        out = torch.empty((B, H, W, stride), dtype=torch.float32, device=x.device)
+        if stride != cout:
+            out.zero_()
+    ops.gconv(x.view(-1, cin), weight_packed, scale, shift, out.view(-1, out.shape[-1]), mode=ops.GCONV_CONV2D,
+              taps=taps, cin=cin, cout=cout, relu=relu, rows_cap=B * H * W, batch=B, H=H, W=W, precision=precision)
+    return out
+
+
+class BEVNet(nn.Module):
+    """cmn.py:233-282.  conv{i}/bn{i} hold the reference-named parameters; compute is NHWC."""
+
+    def __init__(self, in_features, num_filters=256):
+        super().__init__()
+        for i in range(8):
+            k = 1 if i == 7 else 3
+            setattr(self, "conv%d" % i, nn.Conv2d(in_features if i == 0 else num_filters, num_filters, k,
+                                                  padding=k // 2, bias=False))
+            setattr(self, "bn%d" % i, nn.BatchNorm2d(num_filters, eps=1e-3, momentum=0.01))
+        self.num_filters = num_filters
+        self.precision = ops.PREC_FP32
+        self._packed = {}
+
+    def _weights(self, i, dc_order):
+        conv = getattr(self, "conv%d" % i)
+        key = (i, dc_order)
+        ver = _versions(conv.weight)
+        c = self._packed.get(key)
+        if c is None or c[0] != ver:
+            c = (ver, pack_conv2d_weight(conv.weight, dc_order))
+            self._packed[key] = c
+        return c[1]
+
+    def forward_nhwc(self, x, dc_order=None):
+        """x [B,H,W,Cin] (channel order d*C+c when dc_order=(C,D)).  Returns (x, conv6) NHWC."""
+        if self.training:
+            raise NotImplementedError("sassd_b200 is inference-only: call .eval()")
+        for i in range(7):
+            scale, shift = fold_bn(getattr(self, "bn%d" % i))
+            x = conv2d_nhwc(x, self._weights(i, dc_order if i == 0 else None), scale, shift, True, self.num_filters,
+                            self.precision)
+        conv6 = x
+        scale, shift = fold_bn(self.bn7)
+        x = conv2d_nhwc(x, self._weights(7, None), scale, shift, True, self.num_filters, self.precision)
+        return x, conv6
+
+    def forward(self, x):
+        """Reference signature: x [B, Cin, H, W] -> (x, conv6), both [B, 256, H, W] (channels-last storage)."""
+        ops.require_cuda()
+        xh = x.permute(0, 2, 3, 1).contiguous()
+        y, c6 = self.forward_nhwc(xh)
+        return y.permute(0, 3, 1, 2), c6.permute(0, 3, 1, 2)
+
+
+class SpMiddleFHD(nn.Module):
+    """cmn.py:12-29,102-119.  Constructor kwargs as in configs/car_cfg.py:10-15."""
+
+    def __init__(self, output_shape, num_input_features=4, num_hidden_features=128):
+        super().__init__()
+        self.sparse_shape = list(output_shape)
+        self.backbone = VxNet(num_input_features)
+        self.fcn = BEVNet(in_features=num_hidden_features, num_filters=256)
+        # training-only aux head (cmn.py:27-29): parameters kept so reference checkpoints load completely
+        self.point_fc = nn.Linear(160, 64, bias=False)
+        self.point_cls = nn.Linear(64, 1, bias=False)
+        self.point_reg = nn.Linear(64, 3, bias=False)
+        self.row_cap_factor = 4
+
+    def set_precision(self, precision):
+        self.backbone.set_precision(precision)
+        self.fcn.precision = precision
+
+    def forward_nhwc(self, voxel_features, coors, batch_size, d_rows=None, status=None):
+        """Device-side entry: capacity-sized inputs + row counter; returns NHWC (x, conv6) and the tensor."""
+        if self.training:
+            raise NotImplementedError("sassd_b200 is inference-only: call .eval()")
+        x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size, d_rows=d_rows, status=status)
+        x.row_cap_factor = self.row_cap_factor
+        x, middle = self.backbone(x)
+        C = x._features.shape[1]
+        D, H, W = x.spatial_shape
+        bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=x._features.device)
+        ops.sparse_to_bev(x._features, x._indices, x.d_rows, C, D, H, W, bev)
+        y, conv6 = self.fcn.forward_nhwc(bev, dc_order=(C, D))
+        return y, conv6, x
+
+    def forward(self, voxel_features, coors, batch_size, is_test=False, d_rows=None, status=None):
+        if not is_test:
+            raise NotImplementedError("the auxiliary training branch (cmn.py:121-135) is out of scope")
+        y, conv6, x = self.forward_nhwc(voxel_features, coors, batch_size, d_rows, status)
+        return y.permute(0, 3, 1, 2), conv6.permute(0, 3, 1, 2)

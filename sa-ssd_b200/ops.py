@@ -1,0 +1,261 @@
+"""Functional wrappers over the C ABI (include/sassd_b200.h) on torch CUDA tensors.
+
+torch is plumbing here (device memory, streams); every computation is a
+hand-written sm_100a kernel in csrc/.  All wrappers are asynchronous on the
+current torch stream and keep data-dependent sizes on the device (``d_rows``
+style int32 tensors) — nothing in this module synchronises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .lib import GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_FP32, PREC_TF32X3, GConvDesc, VoxelParams, check
+
+NMS_CAP = 4096
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "sassd ops need contiguous CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.SassdError("sassd_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def next_pow2(n):
+    return 1 << max(1, int(math.ceil(math.log2(max(2, n)))))
+
+
+class Workspace:
+    """Grow-only byte buffers keyed by purpose (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device):
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+_WS = Workspace()
+
+
+# ---------------------------------------------------------------------------- voxelize
+def make_voxel_params(voxel_size, pc_range, max_points, max_voxels):
+    vs = np.asarray(voxel_size, np.float32)
+    rg = np.asarray(pc_range, np.float32)
+    grid = np.round((rg[3:] - rg[:3]) / vs).astype(np.int64)   # voxel_generator.py:13-15
+    p = VoxelParams()
+    for j in range(3):
+        p.voxel_size[j] = float(vs[j]); p.range_min[j] = float(rg[j]); p.grid[j] = int(grid[j])
+    p.max_points = int(max_points); p.max_voxels = int(max_voxels)
+    return p, grid
+
+
+def voxelize(points, pt_off, batch, params, rows_cap, slots_per_frame, status, want_mean=True, ws=None):
+    """points [Ncap,4] f32, pt_off [batch+1] i32 (device).  Returns capacity-sized
+    (voxels, coors, num_points, mean, frame_rows[batch+1])."""
+    dev = points.device
+    n_cap = points.shape[0]
+    voxels = torch.empty((rows_cap, params.max_points, 4), dtype=torch.float32, device=dev)
+    coors = torch.empty((rows_cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((rows_cap,), dtype=torch.int32, device=dev)
+    mean = torch.empty((rows_cap, 4), dtype=torch.float32, device=dev) if want_mean else None
+    frame_rows = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    nbytes = _L().sassd_voxelize_workspace_bytes(n_cap, batch, slots_per_frame)
+    w = (ws or _WS).get("voxelize", nbytes, dev)
+    check(_L().sassd_voxelize(_ptr(points), _ptr(pt_off), n_cap, batch, ctypes.byref(params), slots_per_frame,
+                              _ptr(voxels), _ptr(coors), _ptr(num), _ptr(mean), rows_cap, _ptr(frame_rows),
+                              _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_voxelize")
+    return voxels, coors, num, mean, frame_rows
+
+
+def voxel_mean(voxels, num_points, d_rows=None):
+    rows, maxp = voxels.shape[0], voxels.shape[1]
+    mean = torch.empty((rows, 4), dtype=torch.float32, device=voxels.device)
+    check(_L().sassd_voxel_mean(_ptr(voxels), _ptr(num_points), _ptr(d_rows), rows, maxp, _ptr(mean), _stream()),
+          "sassd_voxel_mean")
+    return mean
+
+
+def anchor_mask(coors, d_rows, batch, H, W, rects, threshold=1, ws=None):
+    dev = coors.device
+    na = rects.shape[0]
+    mask = torch.empty((batch, na), dtype=torch.uint8, device=dev)
+    nbytes = _L().sassd_anchor_mask_workspace_bytes(batch, H, W)
+    w = (ws or _WS).get("amask", nbytes, dev)
+    check(_L().sassd_anchor_mask(_ptr(coors), _ptr(d_rows), coors.shape[0], batch, H, W, _ptr(rects), na,
+                                 int(threshold), _ptr(mask), _ptr(w), w.numel(), _stream()), "sassd_anchor_mask")
+    return mask
+
+
+# ---------------------------------------------------------------------------- rulebooks
+class HashIndex:
+    def __init__(self, rows_cap, device):
+        self.slots = next_pow2(2 * max(rows_cap, 1))
+        self.keys = torch.empty((self.slots,), dtype=torch.int32, device=device)
+        self.vals = torch.empty((self.slots,), dtype=torch.int32, device=device)
+
+
+def hash_build(index, coors, d_rows, batch, shape, status):
+    D, H, W = shape
+    check(_L().sassd_hash_build(_ptr(coors), _ptr(d_rows), coors.shape[0], batch, D, H, W, _ptr(index.keys),
+                                _ptr(index.vals), index.slots, _ptr(status), _stream()), "sassd_hash_build")
+    return index
+
+
+def rulebook_subm(coors, d_rows, shape, index, nbr=None):
+    D, H, W = shape
+    rows_cap = coors.shape[0]
+    if nbr is None:
+        nbr = torch.empty((rows_cap, 27), dtype=torch.int32, device=coors.device)
+    check(_L().sassd_rulebook_subm(_ptr(coors), _ptr(d_rows), rows_cap, D, H, W, _ptr(index.keys), _ptr(index.vals),
+                                   index.slots, _ptr(nbr), _stream()), "sassd_rulebook_subm")
+    return nbr
+
+
+def conv_out_shape(shape):
+    return [(s + 2 - 3) // 2 + 1 for s in shape]
+
+
+def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, status, ws=None, ws_key="rbconv"):
+    """Strided (k3,s2,p1) rulebook.  Returns coors_out [cap,4], d_rows_out [1], nbr [cap,27], out_shape."""
+    dev = coors_in.device
+    D, H, W = shape
+    Do, Ho, Wo = conv_out_shape(shape)
+    coors_out = torch.empty((rows_cap_out, 4), dtype=torch.int32, device=dev)
+    d_rows_out = torch.empty((1,), dtype=torch.int32, device=dev)
+    nbr = torch.empty((rows_cap_out, 27), dtype=torch.int32, device=dev)
+    nbytes = _L().sassd_rulebook_conv_workspace_bytes(batch, Do, Ho, Wo)
+    w = (ws or _WS).get(ws_key, nbytes, dev)
+    check(_L().sassd_rulebook_conv_outputs(_ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
+                                           _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(status), _ptr(w),
+                                           w.numel(), _stream()), "sassd_rulebook_conv_outputs")
+    check(_L().sassd_rulebook_conv_nbr(_ptr(coors_out), _ptr(d_rows_out), rows_cap_out, D, H, W, _ptr(index_in.keys),
+                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _stream()),
+          "sassd_rulebook_conv_nbr")
+    return coors_out, d_rows_out, nbr, [Do, Ho, Wo]
+
+
+def rulebook_pairs(nbr, d_rows):
+    rows_cap = nbr.shape[0]
+    pairs = torch.empty((2, 27, rows_cap), dtype=torch.int32, device=nbr.device)
+    num = torch.empty((27,), dtype=torch.int32, device=nbr.device)
+    check(_L().sassd_rulebook_pairs(_ptr(nbr), _ptr(d_rows), rows_cap, _ptr(pairs), _ptr(num), _stream()),
+          "sassd_rulebook_pairs")
+    return pairs, num
+
+
+# ---------------------------------------------------------------------------- gathered conv
+def gconv(inp, weight, scale, shift, out, *, mode, taps, cin, cout, relu, nbr=None, d_rows=None, rows_cap=None,
+          batch=0, H=0, W=0, precision=PREC_FP32):
+    """out[m,:] = act((sum_t in[row(m,t),:] @ W[t]) * scale + shift); see sassd_b200.h."""
+    d = GConvDesc()
+    d.mode, d.precision = mode, precision
+    d.cin, d.cout, d.taps = cin, cout, taps
+    d.in_stride = inp.stride(-2) if inp.dim() >= 2 else cin
+    d.out_stride = out.stride(-2) if out.dim() >= 2 else cout
+    d.rows_cap = int(rows_cap if rows_cap is not None else out.numel() // d.out_stride)
+    d.batch, d.H, d.W = batch, H, W
+    d.relu = 1 if relu else 0
+    check(_L().sassd_gconv(ctypes.byref(d), _ptr_any(inp), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(nbr),
+                           _ptr(d_rows), _ptr_any(out), _stream()), "sassd_gconv")
+    return out
+
+
+def _ptr_any(t):
+    assert t.is_cuda
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def sparse_to_bev(feat, coors, d_rows, C, D, H, W, bev):
+    check(_L().sassd_sparse_to_bev(_ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, _ptr(bev),
+                                   _stream()), "sassd_sparse_to_bev")
+    return bev
+
+
+# ---------------------------------------------------------------------------- head tail
+def decode_select(head, num_class, anchors, mask, thr, k_cap, status, ws=None):
+    """head [B,H,W,stride] NHWC.  Returns boxes [B,k_cap,7], labels, index, d_k [B]."""
+    dev = head.device
+    B, H, W, stride = head.shape
+    na = anchors.shape[0]
+    boxes = torch.empty((B, k_cap, 7), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, k_cap), dtype=torch.int32, device=dev)
+    index = torch.empty((B, k_cap), dtype=torch.int32, device=dev)
+    d_k = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = _L().sassd_decode_select_workspace_bytes(B, na)
+    w = (ws or _WS).get("decode", nbytes, dev)
+    check(_L().sassd_decode_select(_ptr(head), stride, B, H, W, num_class, _ptr(anchors), _ptr(mask), na,
+                                   ctypes.c_float(thr), _ptr(boxes), _ptr(labels), _ptr(index), _ptr(d_k), k_cap,
+                                   _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_decode_select")
+    return boxes, labels, index, d_k
+
+
+def pswarp(feat, boxes, d_k, off_x, off_y, spatial_scale):
+    B, H, W, stride = feat.shape
+    k_cap = boxes.shape[1]
+    scores = torch.empty((B, k_cap), dtype=torch.float32, device=feat.device)
+    check(_L().sassd_pswarp(_ptr(feat), stride, B, H, W, _ptr(boxes), _ptr(d_k), k_cap, ctypes.c_float(off_x),
+                            ctypes.c_float(off_y), ctypes.c_float(spatial_scale), _ptr(scores), _stream()),
+          "sassd_pswarp")
+    return scores
+
+
+def rescore_nms(boxes, scores, labels, d_k, score_thr, iou_thr, det_cap, status, ws=None):
+    dev = boxes.device
+    B, k_cap = boxes.shape[0], boxes.shape[1]
+    det = torch.empty((B, det_cap, 9), dtype=torch.float32, device=dev)
+    d_ndet = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = _L().sassd_rescore_nms_workspace_bytes(B, k_cap, NMS_CAP)
+    w = (ws or _WS).get("nms", nbytes, dev)
+    check(_L().sassd_rescore_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(d_k), B, k_cap,
+                                 ctypes.c_float(score_thr), ctypes.c_float(iou_thr), NMS_CAP, _ptr(det), _ptr(d_ndet),
+                                 det_cap, _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_rescore_nms")
+    return det, d_ndet
+
+
+def nms_mask(boxes5, thr):
+    n = boxes5.shape[0]
+    colb = (n + 63) // 64
+    mask = torch.zeros((n, max(colb, 1)), dtype=torch.int64, device=boxes5.device)
+    check(_L().sassd_nms_mask(_ptr(boxes5), n, ctypes.c_float(thr), _ptr(mask), _stream()), "sassd_nms_mask")
+    return mask[:, :colb]
+
+
+def nms_sorted(boxes5, thr):
+    """boxes sorted by score.  Returns (keep [n] int64 capacity-sized, d_nkeep [1])."""
+    dev = boxes5.device
+    n = boxes5.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    d_n = torch.zeros((1,), dtype=torch.int32, device=dev)
+    nbytes = _L().sassd_nms_workspace_bytes(n)
+    w = _WS.get("nms_sorted", nbytes, dev)
+    check(_L().sassd_nms_sorted(_ptr(boxes5), n, ctypes.c_float(thr), _ptr(keep), _ptr(d_n), _ptr(w), w.numel(),
+                                _stream()), "sassd_nms_sorted")
+    return keep, d_n
+
+
+def boxes_iou_bev(a, b):
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(_L().sassd_boxes_iou_bev(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()),
+          "sassd_boxes_iou_bev")
+    return out

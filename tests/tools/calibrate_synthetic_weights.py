@@ -1,0 +1,105 @@
+"""Dev tool (uses the CPU oracle): calibrate the BatchNorm running statistics of the
+synthetic weights on synthetic frames — what training-mode BN would have recorded — so that
+activations stay O(1) through all 22 conv layers, then report the head statistics used to
+pick cls_gain / cls_bias.  Writes sa-ssd_b200/synth_calib.npz (a few KB, committed).
+
+    python tests/tools/calibrate_synthetic_weights.py [--write] [gain bias]
+"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import torch.nn.functional as F
+from oracle import ref_pipeline as O
+from sassd_b200.checkpoint import make_synthetic_state_dict
+from sassd_b200.synth import synth_cloud
+
+CFG = dict(voxel_size=[0.05, 0.05, 0.1], pc_range=[0, -40., -3., 70.4, 40., 1.], max_points=5, max_voxels=20000,
+           sparse_shape=[40, 1600, 1408],
+           anchor_cfgs=[dict(sizes=[1.6, 3.9, 1.56], anchor_strides=[0.4, 0.4, 1.0], anchor_offsets=[0.2, -39.8, -1.78],
+                             rotations=[0, 1.57])],
+           grid_offsets=(0., 40.), featmap_stride=.4, score_thr=0.3, iou_thr=0.1)
+
+
+def calibrate(sd, seeds=(0, 1, 2)):
+    calib = {}
+
+    def fit(x, name, dims):
+        m = x.mean(dim=dims)
+        v = x.var(dim=dims, unbiased=False)
+        sd[name + ".running_mean"] = m.clone()
+        sd[name + ".running_var"] = v.clone() + 1e-3
+        calib[name + ".running_mean"] = sd[name + ".running_mean"].numpy()
+        calib[name + ".running_var"] = sd[name + ".running_var"].numpy()
+
+    vl, cl, nl = [], [], []
+    for s in seeds:
+        v, c, n = O.points_to_voxel(synth_cloud(s), CFG["voxel_size"], CFG["pc_range"], 5, 20000)
+        vl.append(v); cl.append(c); nl.append(n)
+    voxels, coors, num = O.merge_batch(vl, cl, nl)
+    x = O.simple_voxel(voxels, num)
+    shape = list(CFG["sparse_shape"])
+    p = "neck.backbone."
+    nbr_subm = None
+    for block, idxs, kind, key in O.VXNET_PLAN:
+        if kind == "down":
+            coors, nbr, shape = O.sparse_conv_rulebook(coors, shape)
+            w = sd["%s%s.0.weight" % (p, block)]
+            x = O.indice_conv(x, w.reshape(27, w.shape[3], w.shape[4]), nbr)
+            fit(x, "%s%s.1" % (p, block), 0)
+            x = torch.relu(O.bn_eval(x, sd, "%s%s.1" % (p, block)))
+            nbr_subm = None
+        else:
+            if nbr_subm is None:
+                nbr_subm = O.subm_rulebook(coors, shape)
+            for i in idxs:
+                w = sd["%s%s.%d.weight" % (p, block, i)]
+                x = O.indice_conv(x, w.reshape(27, w.shape[3], w.shape[4]), nbr_subm)
+                fit(x, "%s%s.%d" % (p, block, i + 1), 0)
+                x = torch.relu(O.bn_eval(x, sd, "%s%s.%d" % (p, block, i + 1)))
+    w = sd[p + "extra_conv.0.weight"]
+    x = x @ w.reshape(w.shape[3], w.shape[4])
+    fit(x, p + "extra_conv.1", 0)
+    x = torch.relu(O.bn_eval(x, sd, p + "extra_conv.1"))
+    bev = O.dense_bev(x, coors, shape, len(seeds))
+    p = "neck.fcn."
+    y = bev
+    for i in range(8):
+        y = F.conv2d(y, sd["%sconv%d.weight" % (p, i)], None, padding=1 if i < 7 else 0)
+        fit(y, "%sbn%d" % (p, i), (0, 2, 3))
+        y = torch.relu(O.bn_eval(y, sd, "%sbn%d" % (p, i)))
+        if i == 6:
+            conv6 = y
+    z = F.conv2d(conv6, sd["extra_head.convs.0.weight"], None, padding=1)
+    fit(z, "extra_head.convs.1", (0, 2, 3))
+    return calib
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    gain = float(args[0]) if len(args) > 0 else None
+    bias = float(args[1]) if len(args) > 1 else None
+    kw = {}
+    if gain is not None:
+        kw = dict(cls_gain=gain, cls_bias=bias)
+    if "--write" in sys.argv:
+        sd = make_synthetic_state_dict(0, 1, calibrated=False, **kw)
+        calib = calibrate(sd)
+        np.savez_compressed(os.path.join(ROOT, "sa-ssd_b200", "synth_calib.npz"), **calib)
+        print("wrote synth_calib.npz with", len(calib), "arrays")
+    sd = make_synthetic_state_dict(0, 1, **kw)
+    for seed in (0, 1, 7):
+        st = {}
+        t0 = time.time()
+        det = O.forward_test(sd, [synth_cloud(seed)], CFG, stages=st)
+        t1 = time.time()
+        x = st["x"]; cls = st["cls"]
+        m = torch.as_tensor(st["anchors_mask"][0])
+        logits = cls.reshape(-1)[m]
+        print("seed", seed, "time %.2fs" % (t1 - t0), "M", st["coors"][0].shape[0], "N3", st["coors3"].shape[0],
+              "feat3 std %.3f" % st["feats3"].std(), "x mean %.3f std %.3f" % (x.mean(), x.std()),
+              "mask", int(m.sum()), "logit mean %.3f std %.3f max %.3f" % (logits.mean(), logits.std(), logits.max()),
+              "K", len(st["guided"][0]), "n>0.3", int((torch.sigmoid(st["ps_scores"][0]) > 0.3).sum()),
+              "D", 0 if det[0][0] is None else len(det[0][0]))
+        box = st["box"].reshape(-1, 7)
+        print("   box enc std", box.std(0).numpy().round(3), "ps logit mean %.3f std %.3f" % (st["ps_scores"][0].mean(), st["ps_scores"][0].std()))
