@@ -41,6 +41,32 @@ def next_pow2(n):
     return 1 << max(1, int(math.ceil(math.log2(max(2, n)))))
 
 
+# --- launch accounting / optional per-call CUDA-event timing (bench.py) ---------------
+# kernels launched by each C-ABI entry point (memsets not counted)
+_KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
+            "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
+            "sassd_boxes_iou_bev": 1}
+LAUNCHES = 0          # running count of kernels launched through this module
+PROFILE = None        # set to a list to collect (name, label, start_event, end_event)
+
+
+def _call(name, label, *args):
+    global LAUNCHES
+    LAUNCHES += _KERNELS[name]
+    fn = getattr(_L(), name)
+    if PROFILE is None:
+        check(fn(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), name)
+    e1.record()
+    PROFILE.append((name, label, e0, e1))
+
+
 class Workspace:
     """Grow-only byte buffers keyed by purpose (the C ABI never allocates)."""
 
@@ -82,17 +108,16 @@ def voxelize(points, pt_off, batch, params, rows_cap, slots_per_frame, status, w
     frame_rows = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_voxelize_workspace_bytes(n_cap, batch, slots_per_frame)
     w = (ws or _WS).get("voxelize", nbytes, dev)
-    check(_L().sassd_voxelize(_ptr(points), _ptr(pt_off), n_cap, batch, ctypes.byref(params), slots_per_frame,
+    _call("sassd_voxelize", None, _ptr(points), _ptr(pt_off), n_cap, batch, ctypes.byref(params), slots_per_frame,
                               _ptr(voxels), _ptr(coors), _ptr(num), _ptr(mean), rows_cap, _ptr(frame_rows),
-                              _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_voxelize")
+                              _ptr(status), _ptr(w), w.numel(), _stream())
     return voxels, coors, num, mean, frame_rows
 
 
 def voxel_mean(voxels, num_points, d_rows=None):
     rows, maxp = voxels.shape[0], voxels.shape[1]
     mean = torch.empty((rows, 4), dtype=torch.float32, device=voxels.device)
-    check(_L().sassd_voxel_mean(_ptr(voxels), _ptr(num_points), _ptr(d_rows), rows, maxp, _ptr(mean), _stream()),
-          "sassd_voxel_mean")
+    _call("sassd_voxel_mean", None, _ptr(voxels), _ptr(num_points), _ptr(d_rows), rows, maxp, _ptr(mean), _stream())
     return mean
 
 
@@ -102,8 +127,8 @@ def anchor_mask(coors, d_rows, batch, H, W, rects, threshold=1, ws=None):
     mask = torch.empty((batch, na), dtype=torch.uint8, device=dev)
     nbytes = _L().sassd_anchor_mask_workspace_bytes(batch, H, W)
     w = (ws or _WS).get("amask", nbytes, dev)
-    check(_L().sassd_anchor_mask(_ptr(coors), _ptr(d_rows), coors.shape[0], batch, H, W, _ptr(rects), na,
-                                 int(threshold), _ptr(mask), _ptr(w), w.numel(), _stream()), "sassd_anchor_mask")
+    _call("sassd_anchor_mask", None, _ptr(coors), _ptr(d_rows), coors.shape[0], batch, H, W, _ptr(rects), na,
+                                 int(threshold), _ptr(mask), _ptr(w), w.numel(), _stream())
     return mask
 
 
@@ -117,8 +142,8 @@ class HashIndex:
 
 def hash_build(index, coors, d_rows, batch, shape, status):
     D, H, W = shape
-    check(_L().sassd_hash_build(_ptr(coors), _ptr(d_rows), coors.shape[0], batch, D, H, W, _ptr(index.keys),
-                                _ptr(index.vals), index.slots, _ptr(status), _stream()), "sassd_hash_build")
+    _call("sassd_hash_build", None, _ptr(coors), _ptr(d_rows), coors.shape[0], batch, D, H, W, _ptr(index.keys),
+                                _ptr(index.vals), index.slots, _ptr(status), _stream())
     return index
 
 
@@ -127,8 +152,8 @@ def rulebook_subm(coors, d_rows, shape, index, nbr=None):
     rows_cap = coors.shape[0]
     if nbr is None:
         nbr = torch.empty((rows_cap, 27), dtype=torch.int32, device=coors.device)
-    check(_L().sassd_rulebook_subm(_ptr(coors), _ptr(d_rows), rows_cap, D, H, W, _ptr(index.keys), _ptr(index.vals),
-                                   index.slots, _ptr(nbr), _stream()), "sassd_rulebook_subm")
+    _call("sassd_rulebook_subm", None, _ptr(coors), _ptr(d_rows), rows_cap, D, H, W, _ptr(index.keys), _ptr(index.vals),
+                                   index.slots, _ptr(nbr), _stream())
     return nbr
 
 
@@ -146,12 +171,11 @@ def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, sta
     nbr = torch.empty((rows_cap_out, 27), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_rulebook_conv_workspace_bytes(batch, Do, Ho, Wo)
     w = (ws or _WS).get(ws_key, nbytes, dev)
-    check(_L().sassd_rulebook_conv_outputs(_ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
+    _call("sassd_rulebook_conv_outputs", None, _ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
                                            _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(status), _ptr(w),
-                                           w.numel(), _stream()), "sassd_rulebook_conv_outputs")
-    check(_L().sassd_rulebook_conv_nbr(_ptr(coors_out), _ptr(d_rows_out), rows_cap_out, D, H, W, _ptr(index_in.keys),
-                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _stream()),
-          "sassd_rulebook_conv_nbr")
+                                           w.numel(), _stream())
+    _call("sassd_rulebook_conv_nbr", None, _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, D, H, W, _ptr(index_in.keys),
+                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _stream())
     return coors_out, d_rows_out, nbr, [Do, Ho, Wo]
 
 
@@ -159,8 +183,7 @@ def rulebook_pairs(nbr, d_rows):
     rows_cap = nbr.shape[0]
     pairs = torch.empty((2, 27, rows_cap), dtype=torch.int32, device=nbr.device)
     num = torch.empty((27,), dtype=torch.int32, device=nbr.device)
-    check(_L().sassd_rulebook_pairs(_ptr(nbr), _ptr(d_rows), rows_cap, _ptr(pairs), _ptr(num), _stream()),
-          "sassd_rulebook_pairs")
+    _call("sassd_rulebook_pairs", None, _ptr(nbr), _ptr(d_rows), rows_cap, _ptr(pairs), _ptr(num), _stream())
     return pairs, num
 
 
@@ -176,8 +199,9 @@ def gconv(inp, weight, scale, shift, out, *, mode, taps, cin, cout, relu, nbr=No
     d.rows_cap = int(rows_cap if rows_cap is not None else out.numel() // d.out_stride)
     d.batch, d.H, d.W = batch, H, W
     d.relu = 1 if relu else 0
-    check(_L().sassd_gconv(ctypes.byref(d), _ptr_any(inp), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(nbr),
-                           _ptr(d_rows), _ptr_any(out), _stream()), "sassd_gconv")
+    label = "gconv[%s taps=%d %d->%d]" % (("table", "conv2d", "rows")[mode], taps, cin, cout)
+    _call("sassd_gconv", label, ctypes.byref(d), _ptr_any(inp), _ptr(weight), _ptr(scale), _ptr(shift), _ptr(nbr),
+                           _ptr(d_rows), _ptr_any(out), _stream())
     return out
 
 
@@ -187,8 +211,8 @@ def _ptr_any(t):
 
 
 def sparse_to_bev(feat, coors, d_rows, C, D, H, W, bev):
-    check(_L().sassd_sparse_to_bev(_ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, _ptr(bev),
-                                   _stream()), "sassd_sparse_to_bev")
+    _call("sassd_sparse_to_bev", None, _ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, _ptr(bev),
+                                   _stream())
     return bev
 
 
@@ -204,9 +228,9 @@ def decode_select(head, num_class, anchors, mask, thr, k_cap, status, ws=None):
     d_k = torch.empty((B,), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_decode_select_workspace_bytes(B, na)
     w = (ws or _WS).get("decode", nbytes, dev)
-    check(_L().sassd_decode_select(_ptr(head), stride, B, H, W, num_class, _ptr(anchors), _ptr(mask), na,
+    _call("sassd_decode_select", None, _ptr(head), stride, B, H, W, num_class, _ptr(anchors), _ptr(mask), na,
                                    ctypes.c_float(thr), _ptr(boxes), _ptr(labels), _ptr(index), _ptr(d_k), k_cap,
-                                   _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_decode_select")
+                                   _ptr(status), _ptr(w), w.numel(), _stream())
     return boxes, labels, index, d_k
 
 
@@ -214,9 +238,8 @@ def pswarp(feat, boxes, d_k, off_x, off_y, spatial_scale):
     B, H, W, stride = feat.shape
     k_cap = boxes.shape[1]
     scores = torch.empty((B, k_cap), dtype=torch.float32, device=feat.device)
-    check(_L().sassd_pswarp(_ptr(feat), stride, B, H, W, _ptr(boxes), _ptr(d_k), k_cap, ctypes.c_float(off_x),
-                            ctypes.c_float(off_y), ctypes.c_float(spatial_scale), _ptr(scores), _stream()),
-          "sassd_pswarp")
+    _call("sassd_pswarp", None, _ptr(feat), stride, B, H, W, _ptr(boxes), _ptr(d_k), k_cap, ctypes.c_float(off_x),
+                            ctypes.c_float(off_y), ctypes.c_float(spatial_scale), _ptr(scores), _stream())
     return scores
 
 
@@ -227,9 +250,9 @@ def rescore_nms(boxes, scores, labels, d_k, score_thr, iou_thr, det_cap, status,
     d_ndet = torch.empty((B,), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_rescore_nms_workspace_bytes(B, k_cap, NMS_CAP)
     w = (ws or _WS).get("nms", nbytes, dev)
-    check(_L().sassd_rescore_nms(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(d_k), B, k_cap,
+    _call("sassd_rescore_nms", None, _ptr(boxes), _ptr(scores), _ptr(labels), _ptr(d_k), B, k_cap,
                                  ctypes.c_float(score_thr), ctypes.c_float(iou_thr), NMS_CAP, _ptr(det), _ptr(d_ndet),
-                                 det_cap, _ptr(status), _ptr(w), w.numel(), _stream()), "sassd_rescore_nms")
+                                 det_cap, _ptr(status), _ptr(w), w.numel(), _stream())
     return det, d_ndet
 
 
@@ -237,7 +260,7 @@ def nms_mask(boxes5, thr):
     n = boxes5.shape[0]
     colb = (n + 63) // 64
     mask = torch.zeros((n, max(colb, 1)), dtype=torch.int64, device=boxes5.device)
-    check(_L().sassd_nms_mask(_ptr(boxes5), n, ctypes.c_float(thr), _ptr(mask), _stream()), "sassd_nms_mask")
+    _call("sassd_nms_mask", None, _ptr(boxes5), n, ctypes.c_float(thr), _ptr(mask), _stream())
     return mask[:, :colb]
 
 
@@ -249,13 +272,12 @@ def nms_sorted(boxes5, thr):
     d_n = torch.zeros((1,), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_nms_workspace_bytes(n)
     w = _WS.get("nms_sorted", nbytes, dev)
-    check(_L().sassd_nms_sorted(_ptr(boxes5), n, ctypes.c_float(thr), _ptr(keep), _ptr(d_n), _ptr(w), w.numel(),
-                                _stream()), "sassd_nms_sorted")
+    _call("sassd_nms_sorted", None, _ptr(boxes5), n, ctypes.c_float(thr), _ptr(keep), _ptr(d_n), _ptr(w), w.numel(),
+                                _stream())
     return keep, d_n
 
 
 def boxes_iou_bev(a, b):
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
-    check(_L().sassd_boxes_iou_bev(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()),
-          "sassd_boxes_iou_bev")
+    _call("sassd_boxes_iou_bev", None, _ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream())
     return out
