@@ -150,6 +150,12 @@ typedef struct {
 int sassd_gconv(const sassd_gconv_desc* host_desc, const float* in, const float* weight, const float* scale,
                 const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, sassd_stream_t stream);
 
+/* SASSD_PREC_TF32X3 takes its weights pre-split (tf32 hi / lo) and pre-swizzled for the tensor-core
+ * shared-memory layout: pack once per layer with sassd_gconv_pack_tf32x3 (weight [taps,cin,cout] ->
+ * packed, sassd_gconv_pack_bytes bytes) and pass `packed` as `weight`. */
+size_t sassd_gconv_pack_bytes(int taps, int cin, int cout);
+int sassd_gconv_pack_tf32x3(const float* weight, int taps, int cin, int cout, float* packed, sassd_stream_t stream);
+
 /* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
  * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;
  * the permutation is folded into the first BEV conv's weights).  The map must be

@@ -1,7 +1,420 @@
-// tcgen05 (3xTF32) path of the gathered implicit-GEMM convolution — placeholder until the
-// tensor-core kernel lands; the entry point reports UNSUPPORTED so that callers fail loudly.
+// Gathered implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, sm_100a),
+// fp32-accurate through a 3xTF32 split (SASSD_PREC_TF32X3).
+//
+//   out[m, :] = act( (sum_t  in[row(m,t), :] @ W[t]) * scale + shift )
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-3  epilogue  : tcgen05.ld accumulator (TMEM) -> BN scale/shift, ReLU -> global rows
+//   warps 4-7  A producer: each thread owns one of the tile's 128 output rows; per (tap, 32-channel
+//                          chunk) it gathers the 128 B of its input row (neighbour table / 3x3
+//                          window / identity), splits every fp32 into tf32 hi + lo and stores both
+//                          into 128B-swizzled K-major shared-memory tiles (generic proxy ->
+//                          fence.proxy.async -> mbarrier)
+//   warp  8    MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8):
+//                          lo*hi + hi*lo + hi*hi per K step, accumulating in TMEM across all taps
+//   warp  9    B loader  : cp.async.bulk (TMA 1-D) of the pre-split, pre-swizzled weight block
+// Pipelines: smem stages (full_a/full_b/empty mbarriers) and two TMEM accumulators
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Why 3xTF32: tcgen05 has no fp32-input MMA and one TF32 pass (10-bit mantissa) cannot hold the
+// 1e-4 parity bar across 22 layers; hi = x with the 13 low mantissa bits cleared, lo = x - hi
+// (exact), and a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi leaves ~2^-21 relative error per product.
 #include "common.cuh"
-int sassd_gconv_tc(const sassd_gconv_desc*, const float*, const float*, const float*, const float*, const int32_t*,
-                   const int32_t*, float*, cudaStream_t) {
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                   // fp32 elements per chunk = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * 128;   // 16 KB (hi) ; same for lo
+constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 4;
+constexpr int THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 2) * 32;   // 320
+constexpr int WARP_MMA = 8, WARP_BLOAD = 9;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B between
+// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int MODE>
+struct RowMapTC {
+    const int* nbr;
+    int taps, M, H, W;
+    __device__ __forceinline__ int operator()(int m, int t, int x, int y) const {
+        if (m >= M) return -1;
+        if (MODE == SASSD_GCONV_TABLE) return __ldg(&nbr[(size_t)m * taps + t]);
+        if (MODE == SASSD_GCONV_ROWS || taps == 1) return m;
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) return -1;
+        return m + dy * W + dx;
+    }
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_TILE_BYTES = BN * 128;                         // per hi / lo
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;         // two accumulators; power of two
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, const float* __restrict__ scale,
+                const float* __restrict__ shift, const int* __restrict__ nbr, const int* __restrict__ d_rows,
+                float* __restrict__ out, int cin, int cout, int taps, int in_stride, int out_stride, int rows_cap,
+                int H, int W, int relu) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
+    // barriers: full_a[S], full_b[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM address word
+    auto full_a = [&](int s) { return bar_base + 8u * s; };
+    auto full_b = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto empty = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (3 * C::STAGES + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (3 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (3 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = d_rows ? min(__ldg(d_rows), rows_cap) : rows_cap;
+    const int ntiles = (M + BM - 1) / BM;
+    const int kchunks = (cin + BK - 1) / BK;
+    const int nchunks = taps * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_a(s), NUM_PROD_WARPS * 32);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), NUM_EPI_WARPS * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
+        // ===================== A producers =====================
+        const int r = threadIdx.x - NUM_EPI_WARPS * 32;   // tile row 0..127
+        RowMapTC<MODE> rowmap{nbr, taps, M, H, W};
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m = tile * BM + r;
+            int x = 0, y = 0;
+            if (MODE == SASSD_GCONV_CONV2D) { x = m % W; y = (m / W) % H; }
+            for (int t = 0; t < taps; ++t) {
+                const int src = rowmap(m, t, x, y);
+                const float* rowp = in + (size_t)(src < 0 ? 0 : src) * in_stride;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(empty(stage), phase ^ 1u);
+                    float4 v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int k = kc * BK + c * 4;
+                        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (src >= 0 && k < cin) v[c] = __ldg((const float4*)(rowp + k));
+                    }
+                    uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
+                    uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(v[c].x) & 0xFFFFE000u); lo.x = v[c].x - hi.x;
+                        hi.y = __uint_as_float(__float_as_uint(v[c].y) & 0xFFFFE000u); lo.y = v[c].y - hi.y;
+                        hi.z = __uint_as_float(__float_as_uint(v[c].z) & 0xFFFFE000u); lo.z = v[c].z - hi.z;
+                        hi.w = __uint_as_float(__float_as_uint(v[c].w) & 0xFFFFE000u); lo.w = v[c].w - hi.w;
+                        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+                        *(float4*)(a_hi + off) = hi;
+                        *(float4*)(a_lo + off) = lo;
+                    }
+                    fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+                    mbar_arrive(full_a(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == WARP_BLOAD) {
+        // ===================== B loader (weights) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    mbar_wait(empty(stage), phase ^ 1u);
+                    const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
+                    const uint8_t* src = (const uint8_t*)wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
+                    mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
+                    bulk_g2s(dst, src, C::B_TILE_BYTES, full_b(stage));
+                    bulk_g2s(dst + C::B_TILE_BYTES, src + C::B_TILE_BYTES, C::B_TILE_BYTES, full_b(stage));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    mbar_wait(full_a(stage), phase);
+                    mbar_wait(full_b(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
+#pragma unroll
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        const uint32_t ko = (uint32_t)k8 * 32u;     // 8 tf32 = 32 bytes along K inside the swizzle row
+                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+                        mma_tf32(d_tmem, dal, dbh, idesc, (ch | k8) ? 1u : 0u);   // small terms first
+                        mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    mma_commit(empty(stage));                  // frees the smem stage when the MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
+                mma_commit(tmem_full(acc));                    // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0-3; TMEM lane quarter = warp id) =====================
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int r = warp * 32 + lane;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(tmem_full(acc), acc_phase);
+            tc_fence_after();
+            const int m = tile * BM + r;
+            float* orow = out + (size_t)m * out_stride;
+            constexpr int CW = (BN >= 32) ? 32 : 16;           // columns per tcgen05.ld
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CW) {
+                uint32_t v[CW];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
+                if constexpr (CW == 32) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                } else {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                          "=r"(v[15])
+                        : "r"(taddr));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4) {
+                        const int n = c0 + j;
+                        if (n >= cout) break;
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int ne = n + e;
+                            const float sc = (scale && ne < cout) ? __ldg(&scale[ne]) : 1.f;
+                            const float sh = (shift && ne < cout) ? __ldg(&shift[ne]) : 0.f;
+                            float val = fmaf(__uint_as_float(v[j + e]), sc, sh);
+                            if (relu) val = fmaxf(val, 0.f);
+                            o[e] = val;
+                        }
+                        if (n + 3 < cout && (out_stride & 3) == 0) {
+                            *(float4*)(orow + n) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < cout) orow[n + e] = o[e];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+template <int MODE, int BN>
+static int launch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
+                  const int* nbr, const int* d_rows, float* out, cudaStream_t stream) {
+    using C = Cfg<BN>;
+    auto kern = gconv_tc_kernel<MODE, BN>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+            return SASSD_ERR_LAUNCH;
+        configured = true;
+    }
+    int grid = sassd_div_up(d->rows_cap, BM);
+    if (grid > 148) grid = 148;
+    kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(in, w, scale, shift, nbr, d_rows, out, d->cin, d->cout, d->taps,
+                                                   d->in_stride, d->out_stride, d->rows_cap, d->H, d->W, d->relu);
+    return sassd_check_launch();
+}
+
+template <int MODE>
+static int dispatch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
+                    const int* nbr, const int* d_rows, float* out, cudaStream_t s) {
+    if (d->cout <= 16) return launch<MODE, 16>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 32) return launch<MODE, 32>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 64) return launch<MODE, 64>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 128) return launch<MODE, 128>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 256) return launch<MODE, 256>(d, in, w, scale, shift, nbr, d_rows, out, s);
     return SASSD_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc
+
+// `weight` for this path is the pre-split, pre-swizzled pack produced by sassd_gconv_pack_tf32x3:
+// [taps*kchunks][hi|lo][BN rows (n)][32 k] fp32, 16-byte chunks XOR-swizzled by (n & 7).
+int sassd_gconv_tc(const sassd_gconv_desc* d, const float* in, const float* weight, const float* scale,
+                   const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, cudaStream_t stream) {
+    switch (d->mode) {
+        case SASSD_GCONV_TABLE: return tc::dispatch<SASSD_GCONV_TABLE>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+        case SASSD_GCONV_CONV2D: return tc::dispatch<SASSD_GCONV_CONV2D>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+        case SASSD_GCONV_ROWS: return tc::dispatch<SASSD_GCONV_ROWS>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+    }
+    return SASSD_ERR_ARG;
+}
+
+// Weight packer (device): W [taps, cin, cout] fp32 -> the layout above.  One thread per packed float.
+__global__ void pack_tf32x3_kernel(const float* __restrict__ w, int taps, int cin, int cout, int bn,
+                                   float* __restrict__ out) {
+    const int kchunks = (cin + 31) / 32;
+    const long long per_chunk = 2LL * bn * 32;
+    const long long total = (long long)taps * kchunks * per_chunk;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long ch = i / per_chunk;
+        long long rem = i % per_chunk;
+        const int part = (int)(rem / (bn * 32));      // 0 = hi, 1 = lo
+        rem %= (bn * 32);
+        const int n = (int)(rem / 32);
+        const int pos = (int)(rem % 32);              // physical position inside the 128-byte row
+        const int chunk16 = pos >> 2, e = pos & 3;
+        const int kk = ((chunk16 ^ (n & 7)) << 2) | e;  // logical k stored at this physical slot
+        const int t = (int)(ch / kchunks), kc = (int)(ch % kchunks);
+        const int k = kc * 32 + kk;
+        float v = 0.f;
+        if (k < cin && n < cout) v = w[((size_t)t * cin + k) * cout + n];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        out[i] = part == 0 ? hi : (v - hi);
+    }
+}
+
+extern "C" size_t sassd_gconv_pack_bytes(int taps, int cin, int cout) {
+    int bn = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+    return (size_t)taps * ((cin + 31) / 32) * 2 * bn * 32 * sizeof(float);
+}
+
+extern "C" int sassd_gconv_pack_tf32x3(const float* weight, int taps, int cin, int cout, float* packed,
+                                       sassd_stream_t stream_) {
+    if (!weight || !packed || taps <= 0 || cin <= 0 || cout <= 0 || cout > 256) return SASSD_ERR_ARG;
+    int bn = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
+    const long long total = (long long)taps * ((cin + 31) / 32) * 2 * bn * 32;
+    pack_tf32x3_kernel<<<sassd_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>(weight, taps, cin, cout, bn, packed);
+    return sassd_check_launch();
 }

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "sassd_rulebook_conv_nbr": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
     "sassd_rulebook_pairs": (c_int, [P, P, c_int, P, P, P]),
     "sassd_gconv": (c_int, [ctypes.POINTER(GConvDesc), P, P, P, P, P, P, P, P]),
+    "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sassd_gconv_pack_tf32x3": (c_int, [P, c_int, c_int, c_int, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, c_int, P,

@@ -1,0 +1,100 @@
+"""GPU dev tool: check the tcgen05 (3xTF32) gathered-GEMM kernel against the FFMA path and fp64,
+smallest cases first, printing diagnostics instead of asserting."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from sassd_b200 import ops
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+
+
+def run(mode, M, cin, cout, taps, relu, H=0, W=0, B=0, nbr=None, d_rows=None, tag="", pattern=None, time_it=False):
+    x = torch.randn(M, cin, device=dev)
+    w = torch.randn(taps, cin, cout, device=dev) * 0.1
+    if pattern == "ones":
+        x.fill_(1.0); w.fill_(0.0); w[:, :, :] = 0.0
+        for n in range(cout):
+            w[0, n % cin, n] = 1.0 + n
+    scale = torch.rand(cout, device=dev) + 0.5
+    shift = torch.randn(cout, device=dev) * 0.1
+    stride = (cout + 3) // 4 * 4
+    outs = []
+    for prec in (ops.PREC_FP32, ops.PREC_TF32X3):
+        out = torch.zeros(M, stride, device=dev)
+        ops.gconv(x, w, scale, shift, out, mode=mode, taps=taps, cin=cin, cout=cout, relu=relu, nbr=nbr, d_rows=d_rows,
+                  rows_cap=M, batch=B, H=H, W=W, precision=prec)
+        torch.cuda.synchronize()
+        outs.append(out[:, :cout].clone())
+    # fp64 reference
+    xd, wd = x.double().cpu(), w.double().cpu()
+    ref = torch.zeros(M, cout, dtype=torch.float64)
+    if mode == ops.GCONV_ROWS or (mode == ops.GCONV_CONV2D and taps == 1):
+        ref = xd @ wd[0]
+    elif mode == ops.GCONV_CONV2D:
+        img = xd.view(B, H, W, cin).permute(0, 3, 1, 2)
+        wk = wd.view(3, 3, cin, cout).permute(3, 2, 0, 1)
+        ref = torch.nn.functional.conv2d(img, wk, padding=1).permute(0, 2, 3, 1).reshape(M, cout)
+    else:
+        nb = nbr.cpu().long()
+        for t in range(taps):
+            o = torch.nonzero(nb[:, t] >= 0).view(-1)
+            ref.index_add_(0, o, xd[nb[o, t]] @ wd[t])
+    ref = ref * scale.double().cpu() + shift.double().cpu()
+    if relu:
+        ref = ref.clamp_min(0)
+    e32 = (outs[0].double().cpu() - ref).abs().max().item()
+    etc = (outs[1].double().cpu() - ref).abs().max().item()
+    sc = ref.abs().max().item()
+    print("%-34s M=%-6d cin=%-3d cout=%-3d taps=%-2d  |ref|max %.3g  err ffma %.2e  err tc %.2e  %s" %
+          (tag, M, cin, cout, taps, sc, e32, etc, "OK" if etc <= 20 * max(e32, 1e-6 * sc) else "MISMATCH"), flush=True)
+    if etc > 20 * max(e32, 1e-6 * sc):
+        d = (outs[1].double().cpu() - ref)
+        bad = torch.nonzero(d.abs() > 1e-3 * max(sc, 1)).cpu()
+        print("   first bad (row, col):", bad[:8].tolist(), " n_bad", bad.shape[0])
+        print("   tc  row0[:8]", outs[1][0, :8].tolist())
+        print("   ref row0[:8]", ref[0, :8].tolist())
+    if time_it:
+        for prec, name in ((ops.PREC_FP32, "ffma"), (ops.PREC_TF32X3, "tc")):
+            out = torch.zeros(M, stride, device=dev)
+            for _ in range(2):
+                ops.gconv(x, w, scale, shift, out, mode=mode, taps=taps, cin=cin, cout=cout, relu=relu, nbr=nbr,
+                          d_rows=d_rows, rows_cap=M, batch=B, H=H, W=W, precision=prec)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.gconv(x, w, scale, shift, out, mode=mode, taps=taps, cin=cin, cout=cout, relu=relu, nbr=nbr,
+                          d_rows=d_rows, rows_cap=M, batch=B, H=H, W=W, precision=prec)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            fl = 2.0 * M * cin * cout * taps
+            print("   %-5s %.3f ms  %.1f TFLOP/s (algorithmic fp32)" % (name, ms, fl / ms / 1e9), flush=True)
+
+
+stage = sys.argv[1] if len(sys.argv) > 1 else "all"
+if stage in ("tiny", "all"):
+    run(ops.GCONV_ROWS, 128, 32, 16, 1, False, tag="rows tiny pattern", pattern="ones")
+    run(ops.GCONV_ROWS, 128, 32, 16, 1, False, tag="rows tiny")
+    run(ops.GCONV_ROWS, 128, 32, 64, 1, True, tag="rows 1 tile N64")
+    run(ops.GCONV_ROWS, 128, 64, 256, 1, True, tag="rows 1 tile N256 2 chunks")
+    run(ops.GCONV_ROWS, 1000, 256, 256, 1, True, tag="rows multi-tile")
+    run(ops.GCONV_ROWS, 1000, 28, 28, 1, False, tag="rows cin=28 (K tail) cout=28")
+    run(ops.GCONV_ROWS, 777, 256, 20, 1, False, tag="rows 256->20")
+if stage in ("conv", "all"):
+    run(ops.GCONV_CONV2D, 2 * 12 * 10, 32, 16, 9, True, H=12, W=10, B=2, tag="conv2d small")
+    run(ops.GCONV_CONV2D, 1 * 40 * 36, 256, 256, 9, True, H=40, W=36, B=1, tag="conv2d 256->256 40x36")
+    run(ops.GCONV_CONV2D, 1 * 40 * 36, 320, 256, 9, True, H=40, W=36, B=1, tag="conv2d 320->256 40x36")
+    run(ops.GCONV_CONV2D, 1 * 40 * 36, 256, 28, 9, True, H=40, W=36, B=1, tag="conv2d 256->28 40x36")
+if stage in ("table", "all"):
+    rs = np.random.RandomState(0)
+    for cin, cout in ((4, 16), (16, 16), (16, 32), (32, 64), (64, 64)):
+        M = 3000
+        nbr = torch.from_numpy(np.where(rs.rand(M, 27) < 0.3, rs.randint(0, M, (M, 27)), -1).astype(np.int32)).to(dev)
+        d_rows = torch.tensor([M - 37], dtype=torch.int32, device=dev)
+        run(ops.GCONV_TABLE, M, cin, cout, 27, True, nbr=nbr, d_rows=None, tag="table %d->%d" % (cin, cout))
+if stage in ("perf", "all"):
+    run(ops.GCONV_CONV2D, 200 * 176, 256, 256, 9, True, H=200, W=176, B=1, tag="BEV 3x3 256->256 B=1", time_it=True)
+    run(ops.GCONV_CONV2D, 4 * 200 * 176, 256, 256, 9, True, H=200, W=176, B=4, tag="BEV 3x3 256->256 B=4", time_it=True)
+print("done")
