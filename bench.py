@@ -174,6 +174,8 @@ def run_ours(args, rank, world, local):
     checkpoint.load_state_dict_into(model, sd)
     if args.precision == "tf32x3":
         model.set_precision(ops.PREC_TF32X3)
+    elif args.precision == "mixed":          # tensor cores for the dense convs, FFMA for the sparse backbone
+        model.set_precision(ops.PREC_TF32X3, sparse=ops.PREC_FP32)
     B = args.batch
     pool = 8
     frames = make_frames(pool * B, first_seed=rank * 1000)      # every rank owns its own frames (weak scaling)
@@ -185,8 +187,16 @@ def run_ours(args, rank, world, local):
         staged.append((hp.to(dev).clone(), ho.to(dev).clone(), max(counts)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    graph = None
+    if not args.no_graph:
+        maxpts = ops.next_pow2(max(max(p.shape[0] for p in fb) for fb in batches))
+        graph = model.enable_cuda_graph(B, maxpts)
+
     def step(i):
         p, o, mx = staged[i % pool]
+        if graph is not None:
+            graph.load_device(p, o)
+            return graph.replay() + (None,)
         return model.forward_device(p, o, B, mx)
 
     for i in range(max(3, args.warmup)):
@@ -209,6 +219,11 @@ def run_ours(args, rank, world, local):
         evs[i][1].record()
     torch.cuda.synchronize()
     launches = (ops.LAUNCHES - l0)
+    if graph is not None:      # launches are inside the captured graph: count the kernels of one eager step
+        l1 = ops.LAUNCHES
+        model.forward_device(*staged[0][:2], B, staged[0][2])
+        torch.cuda.synchronize()
+        launches = (ops.LAUNCHES - l1) * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     # the shard's single exchange step: gather of the fixed-size results (NCCL when world > 1)
     g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
@@ -291,6 +306,7 @@ def run_ours(args, rank, world, local):
                                      "raw points -> detections" % B,
                             frames_per_step=B, weights="synthetic (seed 0, BN calibrated)",
                             l2="flushed between steps (256 MiB memset, untimed)", precision=args.precision,
+                            cuda_graph=graph is not None,
                             parallelism="frames sharded, dp%d" % world),
                 clocks=clocks, gpu_launches=launches,
                 e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
@@ -306,8 +322,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     from sassd_b200 import dist as D
     if args.impl == "reference":

@@ -17,8 +17,8 @@
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Why 3xTF32: tcgen05 has no fp32-input MMA and one TF32 pass (10-bit mantissa) cannot hold the
-// 1e-4 parity bar across 22 layers; hi = x with the 13 low mantissa bits cleared, lo = x - hi
-// (exact), and a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi leaves ~2^-21 relative error per product.
+// 1e-4 parity bar across 22 layers; hi = tf32_rn(x), lo = tf32_rn(x - hi), and
+// a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi leaves ~2^-21 relative error per product.
 #include "common.cuh"
 
 namespace tc {
@@ -94,6 +94,40 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// fp32 -> tf32 with round-to-nearest (the tensor core would otherwise just drop the 13 low bits, which
+// biases every product the same way); lo = tf32_rn(x - hi) is then a signed residual of <= 2^-11 |x|.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t (&v)[CW], uint32_t taddr) {
+    if constexpr (CW == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+    }
+}
+
 template <int MODE>
 struct RowMapTC {
     const int* nbr;
@@ -114,7 +148,12 @@ struct Cfg {
     static constexpr int B_TILE_BYTES = BN * 128;                         // per hi / lo
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
-    static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;         // two accumulators; power of two
+    // per tile two fp32 accumulators of BN columns each: "big" (hi*hi) and "small" (lo*hi + hi*lo).
+    // Tensor-core accumulation truncates (measured: error grows linearly with the number of
+    // accumulate steps, ~2^-24 each); keeping the 2^-11-smaller terms out of the big accumulator
+    // cuts its step count by 3x, and the two are summed once, in fp32 RN, by the epilogue.
+    static constexpr int ACC_BUFS = (4 * BN <= 512) ? 2 : 1;             // double-buffer when TMEM allows
+    static constexpr int TMEM_COLS = (ACC_BUFS * 2 * BN < 32) ? 32 : ACC_BUFS * 2 * BN;   // power of two
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -197,10 +236,10 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         float4 hi, lo;
-                        hi.x = __uint_as_float(__float_as_uint(v[c].x) & 0xFFFFE000u); lo.x = v[c].x - hi.x;
-                        hi.y = __uint_as_float(__float_as_uint(v[c].y) & 0xFFFFE000u); lo.y = v[c].y - hi.y;
-                        hi.z = __uint_as_float(__float_as_uint(v[c].z) & 0xFFFFE000u); lo.z = v[c].z - hi.z;
-                        hi.w = __uint_as_float(__float_as_uint(v[c].w) & 0xFFFFE000u); lo.w = v[c].w - hi.w;
+                        split_tf32(v[c].x, hi.x, lo.x);
+                        split_tf32(v[c].y, hi.y, lo.y);
+                        split_tf32(v[c].z, hi.z, lo.z);
+                        split_tf32(v[c].w, hi.w, lo.w);
                         const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
                         *(float4*)(a_hi + off) = hi;
                         *(float4*)(a_lo + off) = lo;
@@ -239,7 +278,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
                 for (int ch = 0; ch < nchunks; ++ch) {
                     mbar_wait(full_a(stage), phase);
                     mbar_wait(full_b(stage), phase);
@@ -251,15 +290,15 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                         const uint32_t ko = (uint32_t)k8 * 32u;     // 8 tf32 = 32 bytes along K inside the swizzle row
                         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
                         const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        mma_tf32(d_tmem, dal, dbh, idesc, (ch | k8) ? 1u : 0u);   // small terms first
-                        mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                        mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        mma_tf32(d_small, dal, dbh, idesc, (ch | k8) ? 1u : 0u);
+                        mma_tf32(d_small, dah, dbl, idesc, 1u);
+                        mma_tf32(d_big, dah, dbh, idesc, (ch | k8) ? 1u : 0u);
                     }
                     mma_commit(empty(stage));                  // frees the smem stage when the MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 mma_commit(tmem_full(acc));                    // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -275,28 +314,10 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             constexpr int CW = (BN >= 32) ? 32 : 16;           // columns per tcgen05.ld
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CW) {
-                uint32_t v[CW];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
-                if constexpr (CW == 32) {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                } else {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                          "=r"(v[15])
-                        : "r"(taddr));
-                }
+                uint32_t v[CW], u[CW];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 2 * BN + c0);
+                tmem_ld<CW>(v, taddr);
+                tmem_ld<CW>(u, taddr + (uint32_t)BN);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (m < M) {
 #pragma unroll
@@ -309,7 +330,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                             const int ne = n + e;
                             const float sc = (scale && ne < cout) ? __ldg(&scale[ne]) : 1.f;
                             const float sh = (shift && ne < cout) ? __ldg(&shift[ne]) : 0.f;
-                            float val = fmaf(__uint_as_float(v[j + e]), sc, sh);
+                            float val = fmaf(__fadd_rn(__uint_as_float(v[j + e]), __uint_as_float(u[j + e])), sc, sh);
                             if (relu) val = fmaxf(val, 0.f);
                             o[e] = val;
                         }
@@ -325,7 +346,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             }
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
@@ -400,8 +421,9 @@ __global__ void pack_tf32x3_kernel(const float* __restrict__ w, int taps, int ci
         const int k = kc * 32 + kk;
         float v = 0.f;
         if (k < cin && n < cout) v = w[((size_t)t * cin + k) * cout + n];
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        out[i] = part == 0 ? hi : (v - hi);
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        out[i] = part == 0 ? hi : lo;
     }
 }
 

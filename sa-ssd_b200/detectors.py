@@ -46,8 +46,10 @@ class SingleStageDetector(nn.Module):
     def with_rpn(self):
         return hasattr(self, "rpn_head") and self.rpn_head is not None
 
-    def set_precision(self, precision):
-        self.neck.set_precision(precision)
+    def set_precision(self, precision, sparse=None):
+        """ops.PREC_FP32 = CUDA-core FFMA kernels, ops.PREC_TF32X3 = tcgen05 tensor-core kernels (3xTF32 split,
+        fp32-accurate).  ``sparse`` optionally selects a different path for the 13 ruled sparse convs."""
+        self.neck.set_precision(precision, sparse)
         self.rpn_head.precision = precision
         self.extra_head.precision = precision
 
@@ -146,6 +148,17 @@ class SingleStageDetector(nn.Module):
             ho[i + 1] = o
         return hp[:need], ho[:len(counts) + 1], counts
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the fused path
+    def enable_cuda_graph(self, batch, max_points_per_frame=32768):
+        """Capture forward_device once for (batch, max_points_per_frame) and replay it per step: every
+        data-dependent size already lives on the device, so the ~65 launches of a step become one graph
+        launch.  Steps whose shape does not fit fall back to the eager path."""
+        self._graph = _GraphedStep(self, batch, max_points_per_frame)
+        return self._graph
+
+    def disable_cuda_graph(self):
+        self._graph = None
+
     def forward_points(self, points_list, return_aux=False):
         """Raw points in (list of [N_i,>=4] numpy arrays), detections out: per frame a dict of
         boxes_lidar [D,7], scores [D], label_preds [D] (or None entries when nothing survives)."""
@@ -154,9 +167,73 @@ class SingleStageDetector(nn.Module):
             raise RuntimeError("call attach_data_pipeline(voxel_generator, anchor_set) first")
         dev = next(self.parameters()).device
         hp, ho, counts = self.stage_points(points_list)
+        g = getattr(self, "_graph", None)
+        if g is not None and not return_aux and g.fits(len(points_list), counts):
+            bbs, scs, lbs = g.run_host(hp, ho, sum(counts))
+            return [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(bbs, scs, lbs)]
         points = hp.to(dev, non_blocking=True)
         pt_off = ho.to(dev, non_blocking=True)
         det, d_ndet, status, aux = self.forward_device(points, pt_off, len(points_list), max(counts + [1]))
         bbs, scs, lbs = unpack_detections(det, d_ndet, status)
         out = [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(bbs, scs, lbs)]
         return (out, aux) if return_aux else out
+
+
+class _GraphedStep:
+    """One captured step of SingleStageDetector.forward_device with static input/output buffers."""
+
+    def __init__(self, model, batch, max_points_per_frame):
+        dev = next(model.parameters()).device
+        self.model, self.batch, self.maxpts = model, int(batch), int(max_points_per_frame)
+        self.cap = self.batch * self.maxpts
+        self.points = torch.zeros((self.cap, 4), dtype=torch.float32, device=dev)
+        self.pt_off = torch.zeros((self.batch + 1,), dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up: workspaces, weight packs and folded BN get created eagerly
+            for _ in range(2):
+                model.forward_device(self.points, self.pt_off, self.batch, self.maxpts)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.det, self.d_ndet, self.status, self.aux = model.forward_device(self.points, self.pt_off, self.batch,
+                                                                                self.maxpts)
+        self.h_det = torch.empty(self.det.shape, dtype=torch.float32).pin_memory()
+        self.h_nd = torch.empty(self.d_ndet.shape, dtype=torch.int32).pin_memory()
+        self.h_status = torch.empty((1,), dtype=torch.int32).pin_memory()
+
+    def fits(self, batch, counts):
+        return batch == self.batch and max(counts + [0]) <= self.maxpts
+
+    def load_device(self, points, pt_off):
+        """device -> static buffers (for callers whose inputs are already resident)."""
+        self.points[: points.shape[0]].copy_(points, non_blocking=True)
+        self.pt_off.copy_(pt_off, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.det, self.d_ndet, self.status
+
+    def run_host(self, hp, ho, total):
+        """pinned host points in, numpy detections out: H2D, one graph launch, D2H, one stream sync."""
+        self.points[:total].copy_(hp[:total], non_blocking=True)
+        self.pt_off.copy_(ho, non_blocking=True)
+        self.graph.replay()
+        self.h_det.copy_(self.det, non_blocking=True)
+        self.h_nd.copy_(self.d_ndet, non_blocking=True)
+        self.h_status.copy_(self.status, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        word = int(self.h_status[0])
+        if word:
+            raise ops._lib.SassdError("capacity overflow on device: %s" % ops._lib.decode_flags(word))
+        det, n = self.h_det.numpy(), self.h_nd.numpy()
+        bbs, scs, lbs = [], [], []
+        for b in range(det.shape[0]):
+            k = int(n[b])
+            if k == 0:
+                bbs.append(None); scs.append(None); lbs.append(None)
+                continue
+            bbs.append(det[b, :k, :7].copy()); scs.append(det[b, :k, 7].copy())
+            lbs.append(det[b, :k, 8].astype(np.int64))
+        return bbs, scs, lbs

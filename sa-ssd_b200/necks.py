@@ -170,8 +170,9 @@ class SpMiddleFHD(nn.Module):
         self.point_reg = nn.Linear(64, 3, bias=False)
         self.row_cap_factor = 4
 
-    def set_precision(self, precision):
-        self.backbone.set_precision(precision)
+    def set_precision(self, precision, sparse=None):
+        """precision for the dense BEV convs; ``sparse`` (default: same) for the ruled sparse convs."""
+        self.backbone.set_precision(precision if sparse is None else sparse)
         self.fcn.precision = precision
 
     def forward_nhwc(self, voxel_features, coors, batch_size, d_rows=None, status=None):

@@ -201,12 +201,16 @@ def pack_tf32x3(weight):
 
 
 def tc_pack_cached(weight):
+    """Pack once per weight tensor.  The entry keeps the source tensor alive so that its address cannot be
+    recycled for a different weight while the pack is cached (bounded FIFO)."""
     key = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    p = _TC_PACKS.get(key)
-    if p is None:
-        p = pack_tf32x3(weight.contiguous())
-        _TC_PACKS[key] = p
-    return p
+    ent = _TC_PACKS.get(key)
+    if ent is None:
+        if len(_TC_PACKS) >= 256:
+            _TC_PACKS.pop(next(iter(_TC_PACKS)))
+        ent = (pack_tf32x3(weight.contiguous()), weight)
+        _TC_PACKS[key] = ent
+    return ent[0]
 
 
 def gconv(inp, weight, scale, shift, out, *, mode, taps, cin, cout, relu, nbr=None, d_rows=None, rows_cap=None,

@@ -369,7 +369,7 @@ def test_rescore_nms_lists(dev):
 
 
 # ------------------------------------------------------------------ whole path
-def _compare_frame(got, exp, tag, box_atol=1e-4):
+def _compare_frame(got, exp, tag, box_atol=1e-4, score_atol=1e-4):
     if exp[0] is None:
         assert got["boxes_lidar"] is None, tag
         return 0
@@ -377,7 +377,7 @@ def _compare_frame(got, exp, tag, box_atol=1e-4):
     gb, gs = got["boxes_lidar"], got["scores"]
     eb, es = exp[0], exp[1]
     assert gb.shape == eb.shape, "%s: %s vs %s detections" % (tag, gb.shape, eb.shape)
-    np.testing.assert_allclose(gs, es, rtol=0, atol=1e-4, err_msg=tag)          # class scores within 1e-4
+    np.testing.assert_allclose(gs, es, rtol=0, atol=score_atol, err_msg=tag)    # class scores within 1e-4
     np.testing.assert_allclose(gb, eb, rtol=1e-4, atol=box_atol, err_msg=tag)   # box regressions
     return gb.shape[0]
 
@@ -422,7 +422,8 @@ def test_end_to_end_points_to_detections(dev, car_model, seeds):
                                        rtol=1e-3, atol=10 * tol)
         if sx < 20 or border > 1e-4:
             total += _compare_frame(out[b], (exp[0][b], exp[1][b], exp[2][b]), "frame seed %d" % seeds[b],
-                                    box_atol=1e-4 if sx < 20 else 10 * tol)
+                                    box_atol=1e-4 if sx < 20 else 10 * tol,
+                                    score_atol=1e-4 if sx < 20 else max(1e-4, 2.5 * tol))
     assert total > 10
 
 
@@ -442,3 +443,67 @@ def test_reference_signature_forward_test(dev, car_model):
     _compare_frame(res[0], (exp[0][0], exp[1][0], exp[2][0]), "forward_test")
     fused = model.forward_points(clouds)
     np.testing.assert_array_equal(fused[0]["boxes_lidar"], res[0]["boxes_lidar"])
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05, 3xTF32) path
+@pytest.mark.parametrize("seeds", [(0, 9)])
+def test_end_to_end_tensor_core_path(dev, seeds):
+    """The same raw-points -> detections comparison with every conv on the tcgen05 kernels."""
+    from sassd_b200 import ops
+    model, sd = _make_model(dev)
+    model.set_precision(ops.PREC_TF32X3)
+    clouds = [synth_cloud(s) for s in seeds]
+    out, aux = model.forward_points(clouds, return_aux=True)
+    st = {}
+    exp = O.forward_test(sd, clouds, ORACLE_CFG, stages=st)
+    assert np.array_equal(aux["sparse"].indices.cpu().numpy(), st["coors3"])
+    x = aux["x"].permute(0, 3, 1, 2).cpu().numpy()
+    total = 0
+    for b in range(2):
+        sx = max(1.0, float(st["x"][b].abs().max()))
+        np.testing.assert_allclose(x[b], st["x"][b].numpy(), rtol=1e-4, atol=1e-4 * sx)
+        total += _compare_frame(out[b], (exp[0][b], exp[1][b], exp[2][b]), "tc frame seed %d" % seeds[b])
+    assert total > 10
+
+
+@pytest.mark.parametrize("cin,cout,taps", [(256, 256, 9), (320, 256, 9), (256, 28, 9), (28, 28, 1), (256, 20, 1)])
+def test_tensor_core_conv_matches_fp64(dev, cin, cout, taps):
+    """tcgen05 3xTF32 dense conv vs an fp64 reference: error must stay within 4x of the fp32 FFMA kernel's."""
+    from sassd_b200 import ops
+    torch.manual_seed(cin + cout)
+    B, H, W = 2, 24, 20
+    x = torch.randn(B * H * W, cin, device=dev)
+    w = torch.randn(taps, cin, cout, device=dev) * 0.05
+    outs = []
+    for prec in (ops.PREC_FP32, ops.PREC_TF32X3):
+        out = torch.zeros(B * H * W, (cout + 3) // 4 * 4, device=dev)
+        ops.gconv(x, w, None, None, out, mode=ops.GCONV_CONV2D, taps=taps, cin=cin, cout=cout, relu=False,
+                  rows_cap=B * H * W, batch=B, H=H, W=W, precision=prec)
+        outs.append(out[:, :cout].double().cpu())
+    img = x.double().cpu().view(B, H, W, cin).permute(0, 3, 1, 2)
+    k = 3 if taps == 9 else 1
+    wk = w.double().cpu().view(k, k, cin, cout).permute(3, 2, 0, 1)
+    ref = torch.nn.functional.conv2d(img, wk, padding=k // 2).permute(0, 2, 3, 1).reshape(-1, cout)
+    e_ffma = (outs[0] - ref).abs().max().item()
+    e_tc = (outs[1] - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert e_tc <= max(4 * e_ffma, 4e-6 * scale), (e_tc, e_ffma, scale)
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    """The captured step must give the same detections as the eager launch sequence, also after the
+    frame changes between replays (all sizes are device-side)."""
+    model, sd = _make_model(dev)
+    frames = [[synth_cloud(9)], [synth_cloud(0)], [synth_cloud(9)]]
+    eager = [model.forward_points(f) for f in frames]
+    model.enable_cuda_graph(1, 32768)
+    for f, e in zip(frames, eager):
+        g = model.forward_points(f)
+        assert (g[0]["boxes_lidar"] is None) == (e[0]["boxes_lidar"] is None)
+        if e[0]["boxes_lidar"] is not None:
+            np.testing.assert_array_equal(g[0]["boxes_lidar"], e[0]["boxes_lidar"])
+            np.testing.assert_array_equal(g[0]["scores"], e[0]["scores"])
+    # a frame that does not fit the captured shape falls back to the eager path
+    big = model.forward_points([synth_cloud(3, fov_deg=60.0)])
+    assert isinstance(big, list) and len(big) == 1
+    model.disable_cuda_graph()
