@@ -507,3 +507,17 @@ def test_cuda_graph_replay_matches_eager(dev):
     big = model.forward_points([synth_cloud(3, fov_deg=60.0)])
     assert isinstance(big, list) and len(big) == 1
     model.disable_cuda_graph()
+
+
+def test_detect_stream_matches_forward_points(dev):
+    model, sd = _make_model(dev)
+    frames = [[synth_cloud(s)] for s in (9, 0, 6, 9, 0)]
+    ref = [model.forward_points(f) for f in frames]
+    got = list(model.detect_stream(frames, 1, 32768))
+    assert len(got) == len(ref)
+    for g, e in zip(got, ref):
+        assert (g[0]["boxes_lidar"] is None) == (e[0]["boxes_lidar"] is None)
+        if e[0]["boxes_lidar"] is not None:
+            np.testing.assert_array_equal(g[0]["boxes_lidar"], e[0]["boxes_lidar"])
+            np.testing.assert_array_equal(g[0]["scores"], e[0]["scores"])
+            np.testing.assert_array_equal(g[0]["label_preds"], e[0]["label_preds"])
