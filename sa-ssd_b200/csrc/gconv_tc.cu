@@ -219,35 +219,50 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             const int m = tile * BM + r;
             int x = 0, y = 0;
             if (MODE == SASSD_GCONV_CONV2D) { x = m % W; y = (m / W) % H; }
-            for (int t = 0; t < taps; ++t) {
-                const int src = rowmap(m, t, x, y);
-                const float* rowp = in + (size_t)(src < 0 ? 0 : src) * in_stride;
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(empty(stage), phase ^ 1u);
-                    float4 v[8];
+            // software pipeline: the global loads of chunk i+1 are in flight while chunk i waits for its
+            // stage, is split and stored (one L2 round trip per chunk would otherwise serialise the producer)
+            int t = 0, kc = 0;
+            int src = rowmap(m, 0, x, y);
+            int src_nt = taps > 1 ? rowmap(m, 1, x, y) : -1;      // row index of the next tap, fetched one tap ahead
+            float4 vn[8];
+            auto fetch = [&](int s_row, int kchunk) {
+                const float* rowp = in + (size_t)(s_row < 0 ? 0 : s_row) * in_stride;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int k = kc * BK + c * 4;
-                        v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (src >= 0 && k < cin) v[c] = __ldg((const float4*)(rowp + k));
-                    }
-                    uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
-                    uint8_t* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float4 hi, lo;
-                        split_tf32(v[c].x, hi.x, lo.x);
-                        split_tf32(v[c].y, hi.y, lo.y);
-                        split_tf32(v[c].z, hi.z, lo.z);
-                        split_tf32(v[c].w, hi.w, lo.w);
-                        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
-                        *(float4*)(a_hi + off) = hi;
-                        *(float4*)(a_lo + off) = lo;
-                    }
-                    fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-                    mbar_arrive(full_a(stage));
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                for (int c = 0; c < 8; ++c) {
+                    const int k = kchunk * BK + c * 4;
+                    vn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s_row >= 0 && k < cin) vn[c] = __ldg((const float4*)(rowp + k));
                 }
+            };
+            fetch(src, 0);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = vn[c];
+                if (++kc == kchunks) {
+                    kc = 0;
+                    ++t;
+                    src = src_nt;
+                    if (t + 1 < taps) src_nt = rowmap(m, t + 1, x, y);
+                }
+                if (ch + 1 < nchunks) fetch(src, kc);
+                mbar_wait(empty(stage), phase ^ 1u);
+                uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
+                uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 hi, lo;
+                    split_tf32(v[c].x, hi.x, lo.x);
+                    split_tf32(v[c].y, hi.y, lo.y);
+                    split_tf32(v[c].z, hi.z, lo.z);
+                    split_tf32(v[c].w, hi.w, lo.w);
+                    const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+                    *(float4*)(a_hi + off) = hi;
+                    *(float4*)(a_lo + off) = lo;
+                }
+                fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(full_a(stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == WARP_BLOAD) {

@@ -143,7 +143,8 @@ __device__ __forceinline__ float rotated_iou(const float* box_a, const float* bo
 // mask[(frame*n_cap + i) * colb_cap + cb] bit j <=> iou(i, cb*64+j) > thr ; tiles with cb >= rb only.
 // The grid is fixed (CUDA-graph friendly); each CTA walks the frame's live upper-triangle tiles,
 // whose number depends on the device-side candidate count.
-__global__ void __launch_bounds__(64)
+#define NMS_MASK_THREADS 512   // 64 rows x 8 column groups of 8
+__global__ void __launch_bounds__(NMS_MASK_THREADS)
 nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, int n_fixed, int n_cap, int colb_cap,
                 float thr, unsigned long long* __restrict__ mask) {
     const int f = blockIdx.y;
@@ -152,6 +153,8 @@ nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, i
     const int ntiles = colb * (colb + 1) / 2;
     const float* bx = boxes5 + (size_t)f * n_cap * 5;
     __shared__ float s_col[64 * 5];
+    __shared__ unsigned long long s_bits[64];
+    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;   // row in tile, column group
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int rb = 0, rem = t;
         while (rem >= colb - rb) { rem -= colb - rb; ++rb; }
@@ -161,18 +164,23 @@ nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, i
 #pragma unroll
             for (int e = 0; e < 5; ++e) s_col[threadIdx.x * 5 + e] = bx[(size_t)(cb * 64 + threadIdx.x) * 5 + e];
         }
+        if (threadIdx.x < 64) s_bits[threadIdx.x] = 0ULL;
         __syncthreads();
-        if (threadIdx.x < row_size) {
-            const int i = rb * 64 + threadIdx.x;
+        if (r < row_size) {
+            const int i = rb * 64 + r;
             float cur[5];
 #pragma unroll
             for (int e = 0; e < 5; ++e) cur[e] = bx[(size_t)i * 5 + e];
             unsigned long long bits = 0;
-            const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-            for (int j = start; j < col_size; j++)
+            const int start = (rb == cb) ? r + 1 : 0;
+            const int j0 = max(start, g * 8), j1 = min(col_size, g * 8 + 8);
+            for (int j = j0; j < j1; j++)
                 if (rotated_iou(cur, s_col + j * 5) > thr) bits |= 1ULL << j;
-            mask[((size_t)f * n_cap + i) * colb_cap + cb] = bits;
+            if (bits) atomicOr(&s_bits[r], bits);
         }
+        __syncthreads();
+        if (threadIdx.x < row_size)
+            mask[((size_t)f * n_cap + rb * 64 + threadIdx.x) * colb_cap + cb] = s_bits[threadIdx.x];
         __syncthreads();
     }
 }
@@ -378,7 +386,7 @@ extern "C" int sassd_rescore_nms(const float* boxes, const float* scores, const 
     rescore_sort_kernel<kNmsCap><<<batch, RS_THREADS, 0, stream>>>(boxes, scores, d_k, k_cap, score_thr, boxes5,
                                                                    s_sorted, src_sorted, d_n, d_status);
     dim3 grid(128, batch);
-    nms_mask_kernel<<<grid, 64, 0, stream>>>(boxes5, d_n, 0, kNmsCap, COLB, iou_thr, mask);
+    nms_mask_kernel<<<grid, NMS_MASK_THREADS, 0, stream>>>(boxes5, d_n, 0, kNmsCap, COLB, iou_thr, mask);
     nms_gather_kernel<kNmsCap><<<batch, 256, 0, stream>>>(mask, d_n, boxes, labels, k_cap, s_sorted, src_sorted, det,
                                                           d_ndet, det_cap);
     return sassd_check_launch();
@@ -396,7 +404,7 @@ extern "C" int sassd_nms_mask(const float* boxes5, int n, float thr, uint64_t* m
     cudaMemsetAsync(mask, 0, (size_t)n * colb * 8, (cudaStream_t)stream_);
     const long long ntiles = (long long)colb * (colb + 1) / 2;
     dim3 grid((unsigned)(ntiles < 148 * 16 ? ntiles : 148 * 16), 1);
-    nms_mask_kernel<<<grid, 64, 0, (cudaStream_t)stream_>>>(boxes5, nullptr, n, n, colb, thr,
+    nms_mask_kernel<<<grid, NMS_MASK_THREADS, 0, (cudaStream_t)stream_>>>(boxes5, nullptr, n, n, colb, thr,
                                                             (unsigned long long*)mask);
     return sassd_check_launch();
 }
