@@ -63,6 +63,30 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// multicast variant: the same bytes land at the same shared-memory offset of every CTA in `mask` and
+// complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B between
 // 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
@@ -157,7 +181,11 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int MODE, int BN>
+// CL = thread-block cluster size (1, 2 or 4).  With CL > 1 the CTAs of a cluster walk the same
+// (tap, chunk) sequence on different row tiles and share the weight stream: CTA r fetches the r-th
+// 1/CL slice of every weight block and multicasts it to all CTAs of the cluster, which divides the
+// L2 -> SM weight traffic (the dominant term at M=128 tiles: 64 KB of B per 16 KB of A) by CL.
+template <int MODE, int BN, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, const float* __restrict__ scale,
                 const float* __restrict__ shift, const int* __restrict__ nbr, const int* __restrict__ d_rows,
@@ -180,15 +208,20 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = d_rows ? min(__ldg(d_rows), rows_cap) : rows_cap;
-    const int ntiles = (M + BM - 1) / BM;
+    const int ntiles_real = (M + BM - 1) / BM;
+    // every CTA of a cluster must run the same number of tile iterations (they hand each other weight
+    // slices and stage-release signals); tiles past the end are computed on zero rows and never stored
+    const int ntiles = CL > 1 ? ((ntiles_real + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x : ntiles_real;
     const int kchunks = (cin + BK - 1) / BK;
     const int nchunks = taps * kchunks;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_a(s), NUM_PROD_WARPS * 32);
             mbar_init(full_b(s), 1);
-            mbar_init(empty(s), 1);
+            mbar_init(empty(s), CL);      // one tcgen05.commit per CTA of the cluster
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
@@ -204,6 +237,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // peers' barriers must exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -275,9 +309,14 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                     mbar_wait(empty(stage), phase ^ 1u);
                     const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
                     const uint8_t* src = (const uint8_t*)wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
-                    mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
-                    bulk_g2s(dst, src, C::B_TILE_BYTES, full_b(stage));
-                    bulk_g2s(dst + C::B_TILE_BYTES, src + C::B_TILE_BYTES, C::B_TILE_BYTES, full_b(stage));
+                    mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);      // all slices, own and peers'
+                    if (CL == 1) {
+                        bulk_g2s(dst, src, C::B_TILE_BYTES, full_b(stage));
+                        bulk_g2s(dst + C::B_TILE_BYTES, src + C::B_TILE_BYTES, C::B_TILE_BYTES, full_b(stage));
+                    } else {
+                        constexpr uint32_t kSlice = 2 * C::B_TILE_BYTES / CL;
+                        bulk_g2s_mc(dst + cta_rank * kSlice, src + cta_rank * kSlice, kSlice, full_b(stage), kClusterMask);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -309,7 +348,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                         mma_tf32(d_small, dah, dbl, idesc, 1u);
                         mma_tf32(d_big, dah, dbh, idesc, (ch | k8) ? 1u : 0u);
                     }
-                    mma_commit(empty(stage));                  // frees the smem stage when the MMAs retire
+                    // frees the smem stage (in every CTA of the cluster) when the MMAs retire
+                    if (CL == 1) mma_commit(empty(stage)); else mma_commit_mc(empty(stage), kClusterMask);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 mma_commit(tmem_full(acc));                    // accumulator complete -> epilogue
@@ -367,6 +407,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // no CTA may exit while a peer can still signal its barriers
     if (warp == WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
@@ -374,22 +415,43 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     }
 }
 
-template <int MODE, int BN>
-static int launch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
-                  const int* nbr, const int* d_rows, float* out, cudaStream_t stream) {
+template <int MODE, int BN, int CL>
+static int launch_cl(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
+                     const int* nbr, const int* d_rows, float* out, cudaStream_t stream, int grid) {
     using C = Cfg<BN>;
-    auto kern = gconv_tc_kernel<MODE, BN>;
+    auto kern = gconv_tc_kernel<MODE, BN, CL>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
             return SASSD_ERR_LAUNCH;
         configured = true;
     }
-    int grid = sassd_div_up(d->rows_cap, BM);
-    if (grid > 148) grid = 148;
-    kern<<<grid, THREADS, C::SMEM_BYTES, stream>>>(in, w, scale, shift, nbr, d_rows, out, d->cin, d->cout, d->taps,
-                                                   d->in_stride, d->out_stride, d->rows_cap, d->H, d->W, d->relu);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, in, w, scale, shift, nbr, d_rows, out, d->cin, d->cout, d->taps, d->in_stride,
+                           d->out_stride, d->rows_cap, d->H, d->W, d->relu) != cudaSuccess)
+        return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
+}
+
+template <int MODE, int BN>
+static int launch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
+                  const int* nbr, const int* d_rows, float* out, cudaStream_t stream) {
+    const int tiles = sassd_div_up(d->rows_cap, BM);
+    // dense maps with at least one tile per SM: clusters of 4 share the weight stream (148 = 4 x 37)
+    if (MODE != SASSD_GCONV_TABLE && tiles >= 148 && BN >= 32)
+        return launch_cl<MODE, BN, 4>(d, in, w, scale, shift, nbr, d_rows, out, stream, 148);
+    return launch_cl<MODE, BN, 1>(d, in, w, scale, shift, nbr, d_rows, out, stream, tiles < 148 ? tiles : 148);
 }
 
 template <int MODE>

@@ -37,6 +37,7 @@ class SingleStageDetector(nn.Module):
         self.voxel_generator = None      # fused path: attach_data_pipeline()
         self.anchor_set = None
         self._pinned = None
+        self._mask_stream = None
         if isinstance(pretrained, str):
             from .checkpoint import load_params_from_file
             load_params_from_file(self, pretrained)
@@ -118,8 +119,15 @@ class SingleStageDetector(nn.Module):
         vg, aset = self.voxel_generator, self.anchor_set
         voxels, coors, num, mean, frame_rows = vg.generate_device(points, pt_off, batch, max_points_per_frame, status)
         d_rows = frame_rows[batch:batch + 1]
-        mask = aset.mask_device(coors, d_rows, batch)
+        # anchors_mask only feeds the guided-anchor selection: run it on a side stream, next to the backbone
+        main = torch.cuda.current_stream()
+        if self._mask_stream is None:
+            self._mask_stream = torch.cuda.Stream(device=dev)
+        self._mask_stream.wait_stream(main)
+        with torch.cuda.stream(self._mask_stream):
+            mask = aset.mask_device(coors, d_rows, batch)
         y, conv6, xs = self.neck.forward_nhwc(mean, coors, batch, d_rows=d_rows, status=status)
+        main.wait_stream(self._mask_stream)
         head = self.rpn_head.forward_nhwc(y)
         anchors, _ = aset.device_tensors()
         boxes, labels, index, d_k = self.rpn_head.guided_anchors_device(head, anchors, mask, self.guided_thr, status)

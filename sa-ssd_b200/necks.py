@@ -85,6 +85,33 @@ class VxNet(nn.Module):
             if isinstance(m, spconv._SparseConvBase):
                 m.precision = precision
 
+    def prebuild_rulebooks(self, x, side_stream):
+        """All seven rulebooks depend on coordinates only, never on features: build the whole chain
+        (hash -> SubM table -> strided output set -> next hash ...) on ``side_stream`` so that it overlaps the
+        feature convolutions, which wait on each rulebook's event when they first use it."""
+        main = torch.cuda.current_stream()
+        side_stream.wait_stream(main)
+        dev = x._features.device
+        with torch.cuda.stream(side_stream):
+            coors, d_rows, shape, cap = x._indices, x.d_rows, x.spatial_shape, x.rows_cap
+            index = ops.hash_build(ops.HashIndex(cap, dev), coors, d_rows, x.batch_size, shape, x.status)
+            x._index = index
+            for lvl in range(4):
+                nbr = ops.rulebook_subm(coors, d_rows, shape, index)
+                ev = torch.cuda.Event(); ev.record(side_stream)
+                x.indice_dict["subm%d" % lvl] = spconv.Rulebook(nbr, coors, d_rows, shape, index, ev)
+                if lvl == 3:
+                    break
+                D, H, W = ops.conv_out_shape(shape)
+                cap = max(1, min(int(cap * x.row_cap_factor), x.batch_size * D * H * W))
+                co, dn, nbr2, so = ops.rulebook_conv(coors, d_rows, x.batch_size, shape, index, cap, x.status,
+                                                     ws_key="rbconv%d" % lvl)
+                index = ops.hash_build(ops.HashIndex(cap, dev), co, dn, x.batch_size, so, x.status)
+                ev = torch.cuda.Event(); ev.record(side_stream)
+                x.indice_dict["down%d" % lvl] = spconv.Rulebook(nbr2, co, dn, so, index, ev)
+                coors, d_rows, shape = co, dn, so
+        x._rulebook_stream = side_stream   # keep the stream (and its tensors) alive with the tensor
+
 
 def pack_conv2d_weight(w, dc_order=None):
     """[Cout, Cin, kh, kw] -> [taps, Cin, Cout] (tap = ky*3+kx).  ``dc_order=(C, D)`` re-orders
@@ -169,6 +196,8 @@ class SpMiddleFHD(nn.Module):
         self.point_cls = nn.Linear(64, 1, bias=False)
         self.point_reg = nn.Linear(64, 3, bias=False)
         self.row_cap_factor = 4
+        self.overlap_rulebooks = True     # build the rulebook chain on a side stream, concurrently with the convs
+        self._side = None
 
     def set_precision(self, precision, sparse=None):
         """precision for the dense BEV convs; ``sparse`` (default: same) for the ruled sparse convs."""
@@ -181,7 +210,13 @@ class SpMiddleFHD(nn.Module):
             raise NotImplementedError("sassd_b200 is inference-only: call .eval()")
         x = spconv.SparseConvTensor(voxel_features, coors, self.sparse_shape, batch_size, d_rows=d_rows, status=status)
         x.row_cap_factor = self.row_cap_factor
+        if self.overlap_rulebooks:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=x._features.device)
+            self.backbone.prebuild_rulebooks(x, self._side)
         x, middle = self.backbone(x)
+        if self.overlap_rulebooks:
+            torch.cuda.current_stream().wait_stream(self._side)   # join (also required to end a graph capture)
         C = x._features.shape[1]
         D, H, W = x.spatial_shape
         bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=x._features.device)

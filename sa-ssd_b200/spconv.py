@@ -19,8 +19,10 @@ from . import ops
 class Rulebook:
     """nbr [rows_cap, 27] + the output coordinate set of one indice_key."""
 
-    def __init__(self, nbr, coors_out, d_rows_out, shape_out):
+    def __init__(self, nbr, coors_out, d_rows_out, shape_out, index_out=None, event=None):
         self.nbr, self.coors_out, self.d_rows_out, self.shape_out = nbr, coors_out, d_rows_out, shape_out
+        self.index_out = index_out   # hash index over coors_out when it was prebuilt
+        self.event = event           # recorded on the stream that built the rulebook (None = same stream)
 
     def indice_pairs(self):
         """spconv-v1 tables (indice_pairs [2,27,cap], indice_pair_num [27])."""
@@ -116,7 +118,10 @@ class _SparseConvBase(nn.Module):
     def _rulebook(self, x):
         key = self.indice_key
         if key is not None and key in x.indice_dict:
-            return x.indice_dict[key]
+            rb = x.indice_dict[key]
+            if rb.event is not None:      # built on a side stream: order this stream after it
+                torch.cuda.current_stream().wait_event(rb.event)
+            return rb
         if self.subm:
             nbr = ops.rulebook_subm(x._indices, x.d_rows, x.spatial_shape, x.hash_index())
             rb = Rulebook(nbr, x._indices, x.d_rows, x.spatial_shape)
@@ -150,7 +155,8 @@ class _SparseConvBase(nn.Module):
                   precision=self.precision)
         if self.subm:
             return x._derive(out)
-        return x._derive(out, indices=rb.coors_out, spatial_shape=rb.shape_out, d_rows=rb.d_rows_out, index=None)
+        return x._derive(out, indices=rb.coors_out, spatial_shape=rb.shape_out, d_rows=rb.d_rows_out,
+                         index=rb.index_out)
 
 
 class SubMConv3d(_SparseConvBase):
