@@ -189,6 +189,8 @@ def run_ours(args, rank, world, local):
     checkpoint.load_state_dict_into(model, sd)
     if args.precision == "tf32x3":
         model.set_precision(ops.PREC_TF32X3)
+    elif args.precision == "f16x3":
+        model.set_precision(ops.PREC_F16X3)
     elif args.precision == "mixed":          # tensor cores for the dense convs, FFMA for the sparse backbone
         model.set_precision(ops.PREC_TF32X3, sparse=ops.PREC_FP32)
     B = args.batch
@@ -345,7 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "mixed"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "f16x3", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()

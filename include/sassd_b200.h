@@ -135,10 +135,11 @@ int sassd_rulebook_pairs(const int32_t* nbr, const int32_t* d_rows_out, int rows
  * mode CONV2D: rows are pixels of a [batch,H,W] NHWC map, taps = 3x3 window, zero padding
  * mode ROWS  : taps == 1, row(m,0) = m                (1x1 convs / plain GEMM)
  * weight [taps, Cin, Cout] f32; scale/shift [Cout] (folded BatchNorm or bias); Cin % 4 == 0.
- * precision: SASSD_PREC_FP32 = CUDA-core FFMA; SASSD_PREC_TF32X3 = tcgen05 3xTF32 split.
+ * precision: SASSD_PREC_FP32 = CUDA-core FFMA; SASSD_PREC_TF32X3 / SASSD_PREC_F16X3 = tcgen05 tensor cores with a
+ * 3-product hi/lo split of both operands (tf32: 21 bits, any range; fp16: 22 bits, |x| < 65504, 2x the MMA rate).
  * ---------------------------------------------------------------------- */
 enum { SASSD_GCONV_TABLE = 0, SASSD_GCONV_CONV2D = 1, SASSD_GCONV_ROWS = 2 };
-enum { SASSD_PREC_FP32 = 0, SASSD_PREC_TF32X3 = 1 };
+enum { SASSD_PREC_FP32 = 0, SASSD_PREC_TF32X3 = 1, SASSD_PREC_F16X3 = 2 };
 typedef struct {
     int32_t mode, precision;
     int32_t cin, cout, taps;
@@ -150,11 +151,12 @@ typedef struct {
 int sassd_gconv(const sassd_gconv_desc* host_desc, const float* in, const float* weight, const float* scale,
                 const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, sassd_stream_t stream);
 
-/* SASSD_PREC_TF32X3 takes its weights pre-split (tf32 hi / lo) and pre-swizzled for the tensor-core
- * shared-memory layout: pack once per layer with sassd_gconv_pack_tf32x3 (weight [taps,cin,cout] ->
- * packed, sassd_gconv_pack_bytes bytes) and pass `packed` as `weight`. */
-size_t sassd_gconv_pack_bytes(int taps, int cin, int cout);
-int sassd_gconv_pack_tf32x3(const float* weight, int taps, int cin, int cout, float* packed, sassd_stream_t stream);
+/* The tensor-core precisions take their weights pre-split (hi / lo) and pre-swizzled for the shared-memory
+ * operand layout: pack once per layer with sassd_gconv_pack (weight [taps,cin,cout] fp32 -> packed,
+ * sassd_gconv_pack_bytes bytes) and pass `packed` as `weight`. */
+size_t sassd_gconv_pack_bytes(int taps, int cin, int cout, int precision);
+int sassd_gconv_pack(const float* weight, int taps, int cin, int cout, int precision, void* packed,
+                     sassd_stream_t stream);
 
 /* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
  * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;

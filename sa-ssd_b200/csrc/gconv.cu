@@ -239,7 +239,8 @@ extern "C" int sassd_gconv(const sassd_gconv_desc* d, const float* in, const flo
     if (d->mode == SASSD_GCONV_CONV2D && !(d->taps == 9 || d->taps == 1)) return SASSD_ERR_ARG;
     if (d->mode == SASSD_GCONV_ROWS && d->taps != 1) return SASSD_ERR_ARG;
     if (d->rows_cap == 0) return SASSD_OK;
-    if (d->precision == SASSD_PREC_TF32X3) return sassd_gconv_tc(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+    if (d->precision == SASSD_PREC_TF32X3 || d->precision == SASSD_PREC_F16X3)
+        return sassd_gconv_tc(d, in, weight, scale, shift, nbr, d_rows, out, stream);
     if (d->precision != SASSD_PREC_FP32) return SASSD_ERR_ARG;
     switch (d->mode) {
         case SASSD_GCONV_TABLE: return dispatch_ffma<SASSD_GCONV_TABLE>(d, in, weight, scale, shift, nbr, d_rows, out, stream);

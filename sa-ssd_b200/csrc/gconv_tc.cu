@@ -19,6 +19,10 @@
 // Why 3xTF32: tcgen05 has no fp32-input MMA and one TF32 pass (10-bit mantissa) cannot hold the
 // 1e-4 parity bar across 22 layers; hi = tf32_rn(x), lo = tf32_rn(x - hi), and
 // a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi leaves ~2^-21 relative error per product.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tc {
@@ -101,8 +105,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -113,6 +117,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+template <int PREC>
+__device__ __forceinline__ void mma_any(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    if constexpr (PREC == 0) mma_tf32(tmem_d, da, db, idesc, accum); else mma_f16(tmem_d, da, db, idesc, accum);
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -152,6 +169,29 @@ __device__ __forceinline__ void tmem_ld(uint32_t (&v)[CW], uint32_t taddr) {
     }
 }
 
+// PREC 0 = 3xTF32 (kind::tf32, 32 channels per 128-byte row, K=8 per MMA),
+// PREC 1 = 3xFP16 (kind::f16, 64 channels per row, K=16 per MMA, twice the MMA rate and half the operand bytes).
+// FP16 split: hi = half_rn(x), lo = half_rn((x - hi) * 2048); the residual is scaled into the normal fp16 range,
+// the "small" accumulator therefore carries a factor 2048 that the epilogue removes.  22 significand bits survive
+// (vs 21 for the tf32 split); |x| must stay below 65504 (fp16 range) — activations of this network are O(1..100).
+constexpr float kF16LoScale = 2048.f;
+template <int PREC>
+struct Prec {
+    static constexpr int BKC = PREC == 0 ? 32 : 64;   // input channels per pipeline chunk
+    static constexpr int NF4 = BKC / 4;               // float4 loads per row per chunk
+    static constexpr uint32_t FMT = PREC == 0 ? 2u : 0u;   // UMMA operand format: TF32 = 2, F16 = 0
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_f16(float x, float& hi_as_float, float& lo_scaled) {
+    const __half h = __float2half_rn(x);
+    hi_as_float = __half2float(h);
+    lo_scaled = (x - hi_as_float) * kF16LoScale;
+}
+
 template <int MODE>
 struct RowMapTC {
     const int* nbr;
@@ -185,7 +225,7 @@ struct Cfg {
 // (tap, chunk) sequence on different row tiles and share the weight stream: CTA r fetches the r-th
 // 1/CL slice of every weight block and multicasts it to all CTAs of the cluster, which divides the
 // L2 -> SM weight traffic (the dominant term at M=128 tiles: 64 KB of B per 16 KB of A) by CL.
-template <int MODE, int BN, int CL>
+template <int MODE, int BN, int CL, int PREC>
 __global__ void __launch_bounds__(THREADS, 1)
 gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, const float* __restrict__ scale,
                 const float* __restrict__ shift, const int* __restrict__ nbr, const int* __restrict__ d_rows,
@@ -201,10 +241,11 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     auto full_a = [&](int s) { return bar_base + 8u * s; };
     auto full_b = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
     auto empty = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-    auto tmem_full = [&](int a) { return bar_base + 8u * (3 * C::STAGES + a); };
-    auto tmem_empty = [&](int a) { return bar_base + 8u * (3 * C::STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * C::STAGES + 4);
-    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+    auto empty_a = [&](int s) { return bar_base + 8u * (3 * C::STAGES + s); };   // CTA-local release (A producers)
+    auto tmem_full = [&](int a) { return bar_base + 8u * (4 * C::STAGES + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (4 * C::STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (4 * C::STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = d_rows ? min(__ldg(d_rows), rows_cap) : rows_cap;
@@ -212,7 +253,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     // every CTA of a cluster must run the same number of tile iterations (they hand each other weight
     // slices and stage-release signals); tiles past the end are computed on zero rows and never stored
     const int ntiles = CL > 1 ? ((ntiles_real + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x : ntiles_real;
-    const int kchunks = (cin + BK - 1) / BK;
+    using PR = Prec<PREC>;
+    const int kchunks = (cin + PR::BKC - 1) / PR::BKC;
     const int nchunks = taps * kchunks;
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
     constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
@@ -221,7 +263,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(full_a(s), NUM_PROD_WARPS * 32);
             mbar_init(full_b(s), 1);
-            mbar_init(empty(s), CL);      // one tcgen05.commit per CTA of the cluster
+            mbar_init(empty(s), CL);      // one tcgen05.commit per CTA of the cluster (weight slices)
+            mbar_init(empty_a(s), 1);     // this CTA's own commit (A tiles are private)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
@@ -258,21 +301,46 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             int t = 0, kc = 0;
             int src = rowmap(m, 0, x, y);
             int src_nt = taps > 1 ? rowmap(m, 1, x, y) : -1;      // row index of the next tap, fetched one tap ahead
-            float4 vn[8];
+            float4 vn[PR::NF4];
             auto fetch = [&](int s_row, int kchunk) {
                 const float* rowp = in + (size_t)(s_row < 0 ? 0 : s_row) * in_stride;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int k = kchunk * BK + c * 4;
+                for (int c = 0; c < PR::NF4; ++c) {
+                    const int k = kchunk * PR::BKC + c * 4;
                     vn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s_row >= 0 && k < cin) vn[c] = __ldg((const float4*)(rowp + k));
                 }
             };
             fetch(src, 0);
             for (int ch = 0; ch < nchunks; ++ch) {
-                float4 v[8];
+                // split this chunk (consumes vn), then put the next chunk's loads in flight, then wait/store
+                uint4 ph[8], pl[8];       // 8 x 16-byte chunks of the hi / lo rows
+                if constexpr (PREC == 0) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = vn[c];
+                    for (int c = 0; c < 8; ++c) {
+                        float4 hi, lo;
+                        split_tf32(vn[c].x, hi.x, lo.x);
+                        split_tf32(vn[c].y, hi.y, lo.y);
+                        split_tf32(vn[c].z, hi.z, lo.z);
+                        split_tf32(vn[c].w, hi.w, lo.w);
+                        ph[c] = *reinterpret_cast<const uint4*>(&hi);
+                        pl[c] = *reinterpret_cast<const uint4*>(&lo);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {      // 8 channels (two float4) -> one 16-byte chunk of halfs
+                        float h[8], l[8];
+                        const float4 a = vn[2 * c], b = vn[2 * c + 1];
+                        split_f16(a.x, h[0], l[0]); split_f16(a.y, h[1], l[1]);
+                        split_f16(a.z, h[2], l[2]); split_f16(a.w, h[3], l[3]);
+                        split_f16(b.x, h[4], l[4]); split_f16(b.y, h[5], l[5]);
+                        split_f16(b.z, h[6], l[6]); split_f16(b.w, h[7], l[7]);
+                        ph[c] = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]),
+                                           pack_half2(h[6], h[7]));
+                        pl[c] = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]),
+                                           pack_half2(l[6], l[7]));
+                    }
+                }
                 if (++kc == kchunks) {
                     kc = 0;
                     ++t;
@@ -280,19 +348,14 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                     if (t + 1 < taps) src_nt = rowmap(m, t + 1, x, y);
                 }
                 if (ch + 1 < nchunks) fetch(src, kc);
-                mbar_wait(empty(stage), phase ^ 1u);
+                mbar_wait(empty_a(stage), phase ^ 1u);
                 uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
                 uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 hi, lo;
-                    split_tf32(v[c].x, hi.x, lo.x);
-                    split_tf32(v[c].y, hi.y, lo.y);
-                    split_tf32(v[c].z, hi.z, lo.z);
-                    split_tf32(v[c].w, hi.w, lo.w);
                     const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
-                    *(float4*)(a_hi + off) = hi;
-                    *(float4*)(a_lo + off) = lo;
+                    *(uint4*)(a_hi + off) = ph[c];
+                    *(uint4*)(a_lo + off) = pl[c];
                 }
                 fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
                 mbar_arrive(full_a(stage));
@@ -324,7 +387,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     } else if (warp == WARP_MMA) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+            constexpr uint32_t idesc = make_idesc(BM, BN, PR::FMT);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -340,15 +403,16 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
 #pragma unroll
-                    for (int k8 = 0; k8 < BK / 8; ++k8) {
-                        const uint32_t ko = (uint32_t)k8 * 32u;     // 8 tf32 = 32 bytes along K inside the swizzle row
+                    for (int k8 = 0; k8 < 4; ++k8) {
+                        const uint32_t ko = (uint32_t)k8 * 32u;     // 8 tf32 / 16 fp16 = 32 bytes along K in the swizzle row
                         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
                         const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        mma_tf32(d_small, dal, dbh, idesc, (ch | k8) ? 1u : 0u);
-                        mma_tf32(d_small, dah, dbl, idesc, 1u);
-                        mma_tf32(d_big, dah, dbh, idesc, (ch | k8) ? 1u : 0u);
+                        mma_any<PREC>(d_small, dal, dbh, idesc, (ch | k8) ? 1u : 0u);
+                        mma_any<PREC>(d_small, dah, dbl, idesc, 1u);
+                        mma_any<PREC>(d_big, dah, dbh, idesc, (ch | k8) ? 1u : 0u);
                     }
                     // frees the smem stage (in every CTA of the cluster) when the MMAs retire
+                    mma_commit(empty_a(stage));
                     if (CL == 1) mma_commit(empty(stage)); else mma_commit_mc(empty(stage), kClusterMask);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -385,7 +449,9 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                             const int ne = n + e;
                             const float sc = (scale && ne < cout) ? __ldg(&scale[ne]) : 1.f;
                             const float sh = (shift && ne < cout) ? __ldg(&shift[ne]) : 0.f;
-                            float val = fmaf(__fadd_rn(__uint_as_float(v[j + e]), __uint_as_float(u[j + e])), sc, sh);
+                            const float small = PREC == 0 ? __uint_as_float(u[j + e])
+                                                          : __uint_as_float(u[j + e]) * (1.f / kF16LoScale);
+                            float val = fmaf(__fadd_rn(__uint_as_float(v[j + e]), small), sc, sh);
                             if (relu) val = fmaxf(val, 0.f);
                             o[e] = val;
                         }
@@ -415,11 +481,11 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
     }
 }
 
-template <int MODE, int BN, int CL>
+template <int MODE, int BN, int CL, int PREC>
 static int launch_cl(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
                      const int* nbr, const int* d_rows, float* out, cudaStream_t stream, int grid) {
     using C = Cfg<BN>;
-    auto kern = gconv_tc_kernel<MODE, BN, CL>;
+    auto kern = gconv_tc_kernel<MODE, BN, CL, PREC>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
@@ -444,76 +510,111 @@ static int launch_cl(const sassd_gconv_desc* d, const float* in, const float* w,
     return sassd_check_launch();
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int PREC>
 static int launch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
                   const int* nbr, const int* d_rows, float* out, cudaStream_t stream) {
     const int tiles = sassd_div_up(d->rows_cap, BM);
-    // dense maps with at least one tile per SM: clusters of 4 share the weight stream (148 = 4 x 37)
-    if (MODE != SASSD_GCONV_TABLE && tiles >= 148 && BN >= 32)
-        return launch_cl<MODE, BN, 4>(d, in, w, scale, shift, nbr, d_rows, out, stream, 148);
-    return launch_cl<MODE, BN, 1>(d, in, w, scale, shift, nbr, d_rows, out, stream, tiles < 148 ? tiles : 148);
+    // Dense maps with at least one tile per SM can share the weight stream inside a cluster (CTA r multicasts the
+    // r-th slice of every weight block).  Measured on B200 (round 1, 3xTF32, BEV 3x3 256->256): cluster 2 = same
+    // time as independent CTAs, cluster 4 = 1.8x slower (lock-step stage release with 2 stages) — the kernel is
+    // MMA/shared-memory bound, not L2 bound — so it stays opt-in: SASSD_TC_CLUSTER=2.
+    if constexpr (MODE == SASSD_GCONV_CONV2D && BN == 256) {
+        static int cl = -1;
+        if (cl < 0) { const char* e = getenv("SASSD_TC_CLUSTER"); cl = e ? atoi(e) : 1; }
+        if (cl == 2 && tiles >= 148)
+            return launch_cl<MODE, BN, 2, PREC>(d, in, w, scale, shift, nbr, d_rows, out, stream, 148);
+    }
+    return launch_cl<MODE, BN, 1, PREC>(d, in, w, scale, shift, nbr, d_rows, out, stream, tiles < 148 ? tiles : 148);
 }
 
-template <int MODE>
+template <int MODE, int PREC>
 static int dispatch(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale, const float* shift,
                     const int* nbr, const int* d_rows, float* out, cudaStream_t s) {
-    if (d->cout <= 16) return launch<MODE, 16>(d, in, w, scale, shift, nbr, d_rows, out, s);
-    if (d->cout <= 32) return launch<MODE, 32>(d, in, w, scale, shift, nbr, d_rows, out, s);
-    if (d->cout <= 64) return launch<MODE, 64>(d, in, w, scale, shift, nbr, d_rows, out, s);
-    if (d->cout <= 128) return launch<MODE, 128>(d, in, w, scale, shift, nbr, d_rows, out, s);
-    if (d->cout <= 256) return launch<MODE, 256>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 16) return launch<MODE, 16, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 32) return launch<MODE, 32, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 64) return launch<MODE, 64, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 128) return launch<MODE, 128, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+    if (d->cout <= 256) return launch<MODE, 256, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
     return SASSD_ERR_UNSUPPORTED;
 }
 
-}  // namespace tc
-
-// `weight` for this path is the pre-split, pre-swizzled pack produced by sassd_gconv_pack_tf32x3:
-// [taps*kchunks][hi|lo][BN rows (n)][32 k] fp32, 16-byte chunks XOR-swizzled by (n & 7).
-int sassd_gconv_tc(const sassd_gconv_desc* d, const float* in, const float* weight, const float* scale,
-                   const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, cudaStream_t stream) {
+template <int PREC>
+static int dispatch_mode(const sassd_gconv_desc* d, const float* in, const float* w, const float* scale,
+                         const float* shift, const int* nbr, const int* d_rows, float* out, cudaStream_t s) {
     switch (d->mode) {
-        case SASSD_GCONV_TABLE: return tc::dispatch<SASSD_GCONV_TABLE>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
-        case SASSD_GCONV_CONV2D: return tc::dispatch<SASSD_GCONV_CONV2D>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
-        case SASSD_GCONV_ROWS: return tc::dispatch<SASSD_GCONV_ROWS>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+        case SASSD_GCONV_TABLE: return dispatch<SASSD_GCONV_TABLE, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+        case SASSD_GCONV_CONV2D: return dispatch<SASSD_GCONV_CONV2D, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
+        case SASSD_GCONV_ROWS: return dispatch<SASSD_GCONV_ROWS, PREC>(d, in, w, scale, shift, nbr, d_rows, out, s);
     }
     return SASSD_ERR_ARG;
 }
 
-// Weight packer (device): W [taps, cin, cout] fp32 -> the layout above.  One thread per packed float.
-__global__ void pack_tf32x3_kernel(const float* __restrict__ w, int taps, int cin, int cout, int bn,
-                                   float* __restrict__ out) {
-    const int kchunks = (cin + 31) / 32;
-    const long long per_chunk = 2LL * bn * 32;
+}  // namespace tc
+
+// `weight` for these paths is the pre-split, pre-swizzled pack produced by sassd_gconv_pack:
+//   TF32X3: [taps*ceil(cin/32)][hi|lo][BN rows (n)][32 fp32]   F16X3: [taps*ceil(cin/64)][hi|lo][BN][64 fp16]
+// every row is 128 bytes, its 16-byte chunks XOR-swizzled by (n & 7).
+int sassd_gconv_tc(const sassd_gconv_desc* d, const float* in, const float* weight, const float* scale,
+                   const float* shift, const int32_t* nbr, const int32_t* d_rows, float* out, cudaStream_t stream) {
+    if (d->precision == SASSD_PREC_TF32X3) return tc::dispatch_mode<0>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+    if (d->precision == SASSD_PREC_F16X3) return tc::dispatch_mode<1>(d, in, weight, scale, shift, nbr, d_rows, out, stream);
+    return SASSD_ERR_ARG;
+}
+
+static inline int tc_bn(int cout) { return cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256; }
+
+// Weight packer (device): W [taps, cin, cout] fp32 -> the layouts above.  One thread per packed element.
+template <int PREC>
+__global__ void pack_kernel(const float* __restrict__ w, int taps, int cin, int cout, int bn, void* __restrict__ out_) {
+    constexpr int BKC = tc::Prec<PREC>::BKC;
+    constexpr int EPC = PREC == 0 ? 4 : 8;                // elements per 16-byte chunk
+    const int kchunks = (cin + BKC - 1) / BKC;
+    const long long per_chunk = 2LL * bn * BKC;
     const long long total = (long long)taps * kchunks * per_chunk;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long ch = i / per_chunk;
         long long rem = i % per_chunk;
-        const int part = (int)(rem / (bn * 32));      // 0 = hi, 1 = lo
-        rem %= (bn * 32);
-        const int n = (int)(rem / 32);
-        const int pos = (int)(rem % 32);              // physical position inside the 128-byte row
-        const int chunk16 = pos >> 2, e = pos & 3;
-        const int kk = ((chunk16 ^ (n & 7)) << 2) | e;  // logical k stored at this physical slot
+        const int part = (int)(rem / (bn * BKC));         // 0 = hi, 1 = lo
+        rem %= (bn * BKC);
+        const int n = (int)(rem / BKC);
+        const int pos = (int)(rem % BKC);                 // physical element slot inside the 128-byte row
+        const int chunk16 = pos / EPC, e = pos % EPC;
+        const int kk = ((chunk16 ^ (n & 7)) * EPC) + e;   // logical k stored at this physical slot
         const int t = (int)(ch / kchunks), kc = (int)(ch % kchunks);
-        const int k = kc * 32 + kk;
+        const int k = kc * BKC + kk;
         float v = 0.f;
         if (k < cin && n < cout) v = w[((size_t)t * cin + k) * cout + n];
-        float hi, lo;
-        tc::split_tf32(v, hi, lo);
-        out[i] = part == 0 ? hi : lo;
+        if constexpr (PREC == 0) {
+            float hi, lo;
+            tc::split_tf32(v, hi, lo);
+            ((float*)out_)[i] = part == 0 ? hi : lo;
+        } else {
+            float hi, lo;
+            tc::split_f16(v, hi, lo);
+            ((__half*)out_)[i] = __float2half_rn(part == 0 ? hi : lo);
+        }
     }
 }
 
-extern "C" size_t sassd_gconv_pack_bytes(int taps, int cin, int cout) {
-    int bn = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
-    return (size_t)taps * ((cin + 31) / 32) * 2 * bn * 32 * sizeof(float);
+extern "C" size_t sassd_gconv_pack_bytes(int taps, int cin, int cout, int precision) {
+    const int bn = tc_bn(cout);
+    if (precision == SASSD_PREC_TF32X3) return (size_t)taps * ((cin + 31) / 32) * 2 * bn * 128;
+    if (precision == SASSD_PREC_F16X3) return (size_t)taps * ((cin + 63) / 64) * 2 * bn * 128;
+    return 0;
 }
 
-extern "C" int sassd_gconv_pack_tf32x3(const float* weight, int taps, int cin, int cout, float* packed,
-                                       sassd_stream_t stream_) {
+extern "C" int sassd_gconv_pack(const float* weight, int taps, int cin, int cout, int precision, void* packed,
+                                sassd_stream_t stream_) {
     if (!weight || !packed || taps <= 0 || cin <= 0 || cout <= 0 || cout > 256) return SASSD_ERR_ARG;
-    int bn = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : cout <= 128 ? 128 : 256;
-    const long long total = (long long)taps * ((cin + 31) / 32) * 2 * bn * 32;
-    pack_tf32x3_kernel<<<sassd_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>(weight, taps, cin, cout, bn, packed);
+    const int bn = tc_bn(cout);
+    if (precision == SASSD_PREC_TF32X3) {
+        const long long total = (long long)taps * ((cin + 31) / 32) * 2 * bn * 32;
+        pack_kernel<0><<<sassd_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>(weight, taps, cin, cout, bn, packed);
+    } else if (precision == SASSD_PREC_F16X3) {
+        const long long total = (long long)taps * ((cin + 63) / 64) * 2 * bn * 64;
+        pack_kernel<1><<<sassd_grid(total, 256), 256, 0, (cudaStream_t)stream_>>>(weight, taps, cin, cout, bn, packed);
+    } else {
+        return SASSD_ERR_ARG;
+    }
     return sassd_check_launch();
 }

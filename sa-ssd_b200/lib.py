@@ -22,7 +22,7 @@ class GConvDesc(ctypes.Structure):
 
 
 GCONV_TABLE, GCONV_CONV2D, GCONV_ROWS = 0, 1, 2
-PREC_FP32, PREC_TF32X3 = 0, 1
+PREC_FP32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2
 
 OK = 0
 ERRORS = {-1: "SASSD_ERR_ARG", -2: "SASSD_ERR_LAUNCH", -3: "SASSD_ERR_WORKSPACE", -4: "SASSD_ERR_UNSUPPORTED"}
@@ -44,8 +44,8 @@ _SIGNATURES = {
     "sassd_rulebook_conv_nbr": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
     "sassd_rulebook_pairs": (c_int, [P, P, c_int, P, P, P]),
     "sassd_gconv": (c_int, [ctypes.POINTER(GConvDesc), P, P, P, P, P, P, P, P]),
-    "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "sassd_gconv_pack_tf32x3": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sassd_gconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, c_int, P,

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .lib import GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_FP32, PREC_TF32X3, GConvDesc, VoxelParams, check
+from .lib import (GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_F16X3, PREC_FP32, PREC_TF32X3, GConvDesc, VoxelParams,
+                  check)
 
 NMS_CAP = 4096
 
@@ -45,7 +46,7 @@ def next_pow2(n):
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
             "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
-            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack_tf32x3": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
 LAUNCHES = 0          # running count of kernels launched through this module
@@ -191,24 +192,24 @@ def rulebook_pairs(nbr, d_rows):
 _TC_PACKS = {}
 
 
-def pack_tf32x3(weight):
-    """weight [taps, cin, cout] fp32 (device) -> tensor-core pack (tf32 hi/lo split, 128B-swizzled K-major blocks)."""
+def pack_tc(weight, precision):
+    """weight [taps, cin, cout] fp32 (device) -> tensor-core pack (hi/lo split, 128B-swizzled K-major blocks)."""
     taps, cin, cout = weight.shape
-    nbytes = _L().sassd_gconv_pack_bytes(taps, cin, cout)
-    packed = torch.empty((nbytes // 4,), dtype=torch.float32, device=weight.device)
-    _call("sassd_gconv_pack_tf32x3", None, _ptr(weight), taps, cin, cout, _ptr(packed), _stream())
+    nbytes = _L().sassd_gconv_pack_bytes(taps, cin, cout, precision)
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+    _call("sassd_gconv_pack", None, _ptr(weight), taps, cin, cout, precision, _ptr(packed), _stream())
     return packed
 
 
-def tc_pack_cached(weight):
+def tc_pack_cached(weight, precision):
     """Pack once per weight tensor.  The entry keeps the source tensor alive so that its address cannot be
     recycled for a different weight while the pack is cached (bounded FIFO)."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), precision)
     ent = _TC_PACKS.get(key)
     if ent is None:
         if len(_TC_PACKS) >= 256:
             _TC_PACKS.pop(next(iter(_TC_PACKS)))
-        ent = (pack_tf32x3(weight.contiguous()), weight)
+        ent = (pack_tc(weight.contiguous(), precision), weight)
         _TC_PACKS[key] = ent
     return ent[0]
 
@@ -216,8 +217,8 @@ def tc_pack_cached(weight):
 def gconv(inp, weight, scale, shift, out, *, mode, taps, cin, cout, relu, nbr=None, d_rows=None, rows_cap=None,
           batch=0, H=0, W=0, precision=PREC_FP32):
     """out[m,:] = act((sum_t in[row(m,t),:] @ W[t]) * scale + shift); see sassd_b200.h."""
-    if precision == PREC_TF32X3:
-        weight = tc_pack_cached(weight)
+    if precision in (PREC_TF32X3, PREC_F16X3):
+        weight = tc_pack_cached(weight, precision)
     d = GConvDesc()
     d.mode, d.precision = mode, precision
     d.cin, d.cout, d.taps = cin, cout, taps

@@ -21,7 +21,7 @@ def run(mode, M, cin, cout, taps, relu, H=0, W=0, B=0, nbr=None, d_rows=None, ta
     shift = torch.randn(cout, device=dev) * 0.1
     stride = (cout + 3) // 4 * 4
     outs = []
-    for prec in (ops.PREC_FP32, ops.PREC_TF32X3):
+    for prec in (ops.PREC_FP32, ops.PREC_TF32X3, ops.PREC_F16X3):
         out = torch.zeros(M, stride, device=dev)
         ops.gconv(x, w, scale, shift, out, mode=mode, taps=taps, cin=cin, cout=cout, relu=relu, nbr=nbr, d_rows=d_rows,
                   rows_cap=M, batch=B, H=H, W=W, precision=prec)
@@ -46,9 +46,18 @@ def run(mode, M, cin, cout, taps, relu, H=0, W=0, B=0, nbr=None, d_rows=None, ta
         ref = ref.clamp_min(0)
     e32 = (outs[0].double().cpu() - ref).abs().max().item()
     etc = (outs[1].double().cpu() - ref).abs().max().item()
+    e16 = (outs[2].double().cpu() - ref).abs().max().item()
     sc = ref.abs().max().item()
-    print("%-34s M=%-6d cin=%-3d cout=%-3d taps=%-2d  |ref|max %.3g  err ffma %.2e  err tc %.2e  %s" %
-          (tag, M, cin, cout, taps, sc, e32, etc, "OK" if etc <= 20 * max(e32, 1e-6 * sc) else "MISMATCH"), flush=True)
+    bad16 = e16 > 20 * max(e32, 1e-6 * sc)
+    print("%-34s M=%-6d cin=%-3d cout=%-3d taps=%-2d  |ref|max %.3g  err ffma %.2e  tf32x3 %.2e  f16x3 %.2e  %s" %
+          (tag, M, cin, cout, taps, sc, e32, etc, e16,
+           "OK" if etc <= 20 * max(e32, 1e-6 * sc) and not bad16 else "MISMATCH"), flush=True)
+    if bad16:
+        d = (outs[2].double().cpu() - ref)
+        bad = torch.nonzero(d.abs() > 1e-3 * max(sc, 1)).cpu()
+        print("   f16 first bad (row, col):", bad[:8].tolist(), " n_bad", bad.shape[0])
+        print("   f16 row0[:8]", outs[2][0, :8].tolist())
+        print("   ref row0[:8]", ref[0, :8].tolist())
     if etc > 20 * max(e32, 1e-6 * sc):
         d = (outs[1].double().cpu() - ref)
         bad = torch.nonzero(d.abs() > 1e-3 * max(sc, 1)).cpu()
@@ -56,7 +65,7 @@ def run(mode, M, cin, cout, taps, relu, H=0, W=0, B=0, nbr=None, d_rows=None, ta
         print("   tc  row0[:8]", outs[1][0, :8].tolist())
         print("   ref row0[:8]", ref[0, :8].tolist())
     if time_it:
-        for prec, name in ((ops.PREC_FP32, "ffma"), (ops.PREC_TF32X3, "tc")):
+        for prec, name in ((ops.PREC_FP32, "ffma"), (ops.PREC_TF32X3, "tf32x3"), (ops.PREC_F16X3, "f16x3")):
             out = torch.zeros(M, stride, device=dev)
             for _ in range(2):
                 ops.gconv(x, w, scale, shift, out, mode=mode, taps=taps, cin=cin, cout=cout, relu=relu, nbr=nbr,
@@ -70,7 +79,7 @@ def run(mode, M, cin, cout, taps, relu, H=0, W=0, B=0, nbr=None, d_rows=None, ta
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             fl = 2.0 * M * cin * cout * taps
-            print("   %-5s %.3f ms  %.1f TFLOP/s (algorithmic fp32)" % (name, ms, fl / ms / 1e9), flush=True)
+            print("   %-6s %.3f ms  %.1f TFLOP/s (algorithmic fp32)" % (name, ms, fl / ms / 1e9), flush=True)
 
 
 stage = sys.argv[1] if len(sys.argv) > 1 else "all"
