@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local):
     peaks = load_peaks()
     H, W = 200, 176
     dom = max(prof.items(), key=lambda kv: kv[1]["ms_total_per_step"])
-    bev_key = "gconv[conv2d taps=9 256->256]"
+    bev_key = "conv2d_tma[taps=9 256->256]" if "conv2d_tma[taps=9 256->256]" in prof else "gconv[conv2d taps=9 256->256]"
     bev = prof.get(bev_key)
     roofline = None
     if bev:
@@ -291,15 +291,26 @@ def run_ours(args, rank, world, local):
         per_launch_ms = bev["ms_total_per_step"] / bev["calls_per_step"]
         ach = flops / (per_launch_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roofline = dict(kernel="gconv_ffma_kernel<CONV2D,128,16> (BEVNet 3x3 256->256, %d launches/step)" % bev["calls_per_step"],
+        kname = {"fp32": "gconv_ffma_kernel<CONV2D,128,16>", "tf32x3": "tc::gconv_tc_kernel<CONV2D,256,1,TF32X3>",
+                 "mixed": "tc::gconv_tc_kernel<CONV2D,256,1,TF32X3>",
+                 "f16x3": "tma::conv2d_tma_kernel<256>" if bev_key.startswith("conv2d_tma") else
+                          "tc::gconv_tc_kernel<CONV2D,256,1,F16X3>"}[args.precision]
+        passes = {"fp32": "fp32 FFMA (no tensor cores)", "tf32x3": "3 TF32 MMA passes per algorithmic flop",
+                  "mixed": "3 TF32 MMA passes per algorithmic flop",
+                  "f16x3": "3 FP16 MMA passes per algorithmic flop (ceiling 1/3 of the fp16/bf16 peak)"}[args.precision]
+        roofline = dict(kernel="%s (BEVNet 3x3 256->256, %d launches/step)" % (kname, bev["calls_per_step"]),
                         bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
                         peak_source="%s bf16 dense, sustained" % peaks["source"],
-                        note="fp32 CUDA-core path; the tcgen05 3xTF32 path replaces it (DESIGN.md)",
+                        note="achieved = algorithmic fp32 flops / CUDA-event time; " + passes,
+                        mma_issue_frac=(3.0 if args.precision != "fp32" else 1.0) * ach / peak *
+                                       (2.0 if args.precision in ("tf32x3", "mixed") else 1.0),
                         share_of_step=bev["ms_total_per_step"] / sum(v["ms_total_per_step"] for v in prof.values()))
     sp_bytes, sp_flops, pairs = algorithmic_work(aux, B)
     sp_ms = sum(v["ms_total_per_step"] for k, v in prof.items() if k.startswith("gconv[table"))
+    sp_kernel = {"fp32": "gconv_ffma_kernel<TABLE,...>", "mixed": "gconv_ffma_kernel<TABLE,...>"}.get(
+        args.precision, "tc::gconv_tc_kernel<TABLE,BN,1,%s>" % args.precision.upper())
     sp_ach = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
-    roofline_sparse = dict(kernel="gconv_ffma_kernel<TABLE,...> x13 ruled sparse convs", bound="hbm", achieved=sp_ach,
+    roofline_sparse = dict(kernel=sp_kernel + " x13 ruled sparse convs", bound="hbm", achieved=sp_ach,
                            peak=peaks["hbm_gbs"], unit="GB/s", frac=sp_ach / peaks["hbm_gbs"], traffic=None,
                            algorithmic_bytes_per_step=sp_bytes, flops_per_step=sp_flops, ms_per_step=sp_ms,
                            pairs=pairs, peak_source=peaks["source"])
@@ -347,7 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "f16x3", "mixed"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "f16x3", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()

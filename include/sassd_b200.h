@@ -158,6 +158,24 @@ size_t sassd_gconv_pack_bytes(int taps, int cin, int cout, int precision);
 int sassd_gconv_pack(const float* weight, int taps, int cin, int cout, int precision, void* packed,
                      sassd_stream_t stream);
 
+/* Dense NHWC conv (3x3 pad 1, or 1x1) + folded BatchNorm + ReLU on the "split map" activation format — the
+ * BEVNet / head convolutions (cmn.py:264-282, ssd_rotate_head.py:218-231,424-429) with the activation operand
+ * moved by TMA (cp.async.bulk.tensor) instead of producer warps.  A split map is two fp16 planes
+ * [2][batch][H][W][C] (C % 64 == 0): hi = half(x), lo = half((x - hi) * 2048).  Outputs: fp32 NHWC
+ * (out_f32, stride out_f32_stride) and/or the next layer's split map (out_split, out_split_ch channels, the
+ * channels beyond cout written as zero).  wpack: sassd_gconv_pack(..., SASSD_PREC_F16X3).  16 < cout <= 256. */
+typedef struct {
+    int32_t batch, H, W;
+    int32_t cin, cin_stored;       /* valid / stored input channels */
+    int32_t cout, taps, relu;
+    int32_t out_f32_stride, out_split_ch;
+} sassd_conv2d_desc;
+int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
+                       const float* shift, float* out_f32, void* out_split, sassd_stream_t stream);
+/* dense() of the last sparse tensor straight into a (pre-zeroed) split map [2,batch,H,W,D*C]. */
+int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
+                              int D, int H, int W, int batch, void* bev_split, sassd_stream_t stream);
+
 /* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
  * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;
  * the permutation is folded into the first BEV conv's weights).  The map must be

@@ -19,178 +19,13 @@
 // Why 3xTF32: tcgen05 has no fp32-input MMA and one TF32 pass (10-bit mantissa) cannot hold the
 // 1e-4 parity bar across 22 layers; hi = tf32_rn(x), lo = tf32_rn(x - hi), and
 // a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi leaves ~2^-21 relative error per product.
-#include <cuda_fp16.h>
-
 #include <cstdlib>
 
 #include "common.cuh"
 
+#include "tc_common.cuh"
+
 namespace tc {
-
-constexpr int BM = 128;
-constexpr int BK = 32;                   // fp32 elements per chunk = one 128-byte swizzle row
-constexpr int A_TILE_BYTES = BM * 128;   // 16 KB (hi) ; same for lo
-constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 4;
-constexpr int THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 2) * 32;   // 320
-constexpr int WARP_MMA = 8, WARP_BLOAD = 9;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// multicast variant: the same bytes land at the same shared-memory offset of every CTA in `mask` and
-// complete_tx on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B between
-// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-template <int PREC>
-__device__ __forceinline__ void mma_any(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    if constexpr (PREC == 0) mma_tf32(tmem_d, da, db, idesc, accum); else mma_f16(tmem_d, da, db, idesc, accum);
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// fp32 -> tf32 with round-to-nearest (the tensor core would otherwise just drop the 13 low bits, which
-// biases every product the same way); lo = tf32_rn(x - hi) is then a signed residual of <= 2^-11 |x|.
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rn(x);
-    lo = tf32_rn(x - hi);
-}
-
-template <int CW>
-__device__ __forceinline__ void tmem_ld(uint32_t (&v)[CW], uint32_t taddr) {
-    if constexpr (CW == 32) {
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-    } else {
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
-    }
-}
-
-// PREC 0 = 3xTF32 (kind::tf32, 32 channels per 128-byte row, K=8 per MMA),
-// PREC 1 = 3xFP16 (kind::f16, 64 channels per row, K=16 per MMA, twice the MMA rate and half the operand bytes).
-// FP16 split: hi = half_rn(x), lo = half_rn((x - hi) * 2048); the residual is scaled into the normal fp16 range,
-// the "small" accumulator therefore carries a factor 2048 that the epilogue removes.  22 significand bits survive
-// (vs 21 for the tf32 split); |x| must stay below 65504 (fp16 range) — activations of this network are O(1..100).
-constexpr float kF16LoScale = 2048.f;
-template <int PREC>
-struct Prec {
-    static constexpr int BKC = PREC == 0 ? 32 : 64;   // input channels per pipeline chunk
-    static constexpr int NF4 = BKC / 4;               // float4 loads per row per chunk
-    static constexpr uint32_t FMT = PREC == 0 ? 2u : 0u;   // UMMA operand format: TF32 = 2, F16 = 0
-};
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void split_f16(float x, float& hi_as_float, float& lo_scaled) {
-    const __half h = __float2half_rn(x);
-    hi_as_float = __half2float(h);
-    lo_scaled = (x - hi_as_float) * kF16LoScale;
-}
 
 template <int MODE>
 struct RowMapTC {
@@ -286,7 +121,9 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
 
     if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
         // ===================== A producers =====================
-        const int r = threadIdx.x - NUM_EPI_WARPS * 32;   // tile row 0..127
+        const int pt = threadIdx.x - NUM_EPI_WARPS * 32;
+        const int r = pt & 127;                           // tile row 0..127
+        const int hf = pt >> 7;                           // which half of the row's 128-byte chunk this thread fills
         RowMapTC<MODE> rowmap{nbr, taps, M, H, W};
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
@@ -301,12 +138,13 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             int t = 0, kc = 0;
             int src = rowmap(m, 0, x, y);
             int src_nt = taps > 1 ? rowmap(m, 1, x, y) : -1;      // row index of the next tap, fetched one tap ahead
-            float4 vn[PR::NF4];
+            constexpr int NF4H = PR::NF4 / 2;             // float4 loads per thread per chunk
+            float4 vn[NF4H];
             auto fetch = [&](int s_row, int kchunk) {
                 const float* rowp = in + (size_t)(s_row < 0 ? 0 : s_row) * in_stride;
 #pragma unroll
-                for (int c = 0; c < PR::NF4; ++c) {
-                    const int k = kchunk * PR::BKC + c * 4;
+                for (int c = 0; c < NF4H; ++c) {
+                    const int k = kchunk * PR::BKC + (hf * NF4H + c) * 4;
                     vn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s_row >= 0 && k < cin) vn[c] = __ldg((const float4*)(rowp + k));
                 }
@@ -314,10 +152,10 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             fetch(src, 0);
             for (int ch = 0; ch < nchunks; ++ch) {
                 // split this chunk (consumes vn), then put the next chunk's loads in flight, then wait/store
-                uint4 ph[8], pl[8];       // 8 x 16-byte chunks of the hi / lo rows
+                uint4 ph[4], pl[4];       // this thread's 4 of the 8 16-byte chunks of the hi / lo rows
                 if constexpr (PREC == 0) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < 4; ++c) {
                         float4 hi, lo;
                         split_tf32(vn[c].x, hi.x, lo.x);
                         split_tf32(vn[c].y, hi.y, lo.y);
@@ -328,17 +166,15 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {      // 8 channels (two float4) -> one 16-byte chunk of halfs
-                        float h[8], l[8];
+                    for (int c = 0; c < 4; ++c) {      // 8 channels (two float4) -> one 16-byte chunk of halfs
                         const float4 a = vn[2 * c], b = vn[2 * c + 1];
-                        split_f16(a.x, h[0], l[0]); split_f16(a.y, h[1], l[1]);
-                        split_f16(a.z, h[2], l[2]); split_f16(a.w, h[3], l[3]);
-                        split_f16(b.x, h[4], l[4]); split_f16(b.y, h[5], l[5]);
-                        split_f16(b.z, h[6], l[6]); split_f16(b.w, h[7], l[7]);
-                        ph[c] = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]),
-                                           pack_half2(h[6], h[7]));
-                        pl[c] = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]),
-                                           pack_half2(l[6], l[7]));
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split_f16x2(a.x, a.y, h0, l0);
+                        split_f16x2(a.z, a.w, h1, l1);
+                        split_f16x2(b.x, b.y, h2, l2);
+                        split_f16x2(b.z, b.w, h3, l3);
+                        ph[c] = make_uint4(h0, h1, h2, h3);
+                        pl[c] = make_uint4(l0, l1, l2, l3);
                     }
                 }
                 if (++kc == kchunks) {
@@ -352,8 +188,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                 uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
                 uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = row_off + (((uint32_t)(hf * 4 + c) ^ sw) << 4);
                     *(uint4*)(a_hi + off) = ph[c];
                     *(uint4*)(a_lo + off) = pl[c];
                 }
@@ -374,8 +210,11 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                     const uint8_t* src = (const uint8_t*)wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
                     mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);      // all slices, own and peers'
                     if (CL == 1) {
-                        bulk_g2s(dst, src, C::B_TILE_BYTES, full_b(stage));
-                        bulk_g2s(dst + C::B_TILE_BYTES, src + C::B_TILE_BYTES, C::B_TILE_BYTES, full_b(stage));
+                        // several medium-sized bulk copies in flight move a block faster than one big one
+                        constexpr uint32_t kPiece = (2 * C::B_TILE_BYTES >= 8192) ? 8192u : (uint32_t)(2 * C::B_TILE_BYTES);
+#pragma unroll 1
+                        for (uint32_t o = 0; o < 2u * C::B_TILE_BYTES; o += kPiece)
+                            bulk_g2s(dst + o, src + o, kPiece, full_b(stage));
                     } else {
                         constexpr uint32_t kSlice = 2 * C::B_TILE_BYTES / CL;
                         bulk_g2s_mc(dst + cta_rank * kSlice, src + cta_rank * kSlice, kSlice, full_b(stage), kClusterMask);

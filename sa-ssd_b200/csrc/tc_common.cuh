@@ -1,0 +1,184 @@
+// Device-side helpers shared by the tcgen05 kernels (gconv_tc.cu, conv2d_tma.cu): mbarrier / bulk-copy /
+// tcgen05 PTX wrappers, UMMA descriptors, TMEM loads and the hi/lo operand splits.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                   // fp32 elements per chunk = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * 128;   // 16 KB (hi) ; same for lo
+constexpr int NUM_EPI_WARPS = 4, NUM_PROD_WARPS = 8;   // two producer threads per tile row
+constexpr int THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 2) * 32;   // 448
+constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_PROD_WARPS, WARP_BLOAD = WARP_MMA + 1;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// multicast variant: the same bytes land at the same shared-memory offset of every CTA in `mask` and
+// complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B between
+// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+template <int PREC>
+__device__ __forceinline__ void mma_any(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    if constexpr (PREC == 0) mma_tf32(tmem_d, da, db, idesc, accum); else mma_f16(tmem_d, da, db, idesc, accum);
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// fp32 -> tf32 with round-to-nearest (the tensor core would otherwise just drop the 13 low bits, which
+// biases every product the same way); lo = tf32_rn(x - hi) is then a signed residual of <= 2^-11 |x|.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t (&v)[CW], uint32_t taddr) {
+    if constexpr (CW == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+    }
+}
+
+// PREC 0 = 3xTF32 (kind::tf32, 32 channels per 128-byte row, K=8 per MMA),
+// PREC 1 = 3xFP16 (kind::f16, 64 channels per row, K=16 per MMA, twice the MMA rate and half the operand bytes).
+// FP16 split: hi = half_rn(x), lo = half_rn((x - hi) * 2048); the residual is scaled into the normal fp16 range,
+// the "small" accumulator therefore carries a factor 2048 that the epilogue removes.  22 significand bits survive
+// (vs 21 for the tf32 split); |x| must stay below 65504 (fp16 range) — activations of this network are O(1..100).
+constexpr float kF16LoScale = 2048.f;
+template <int PREC>
+struct Prec {
+    static constexpr int BKC = PREC == 0 ? 32 : 64;   // input channels per pipeline chunk
+    static constexpr int NF4 = BKC / 4;               // float4 loads per row per chunk
+    static constexpr uint32_t FMT = PREC == 0 ? 2u : 0u;   // UMMA operand format: TF32 = 2, F16 = 0
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void split_f16(float x, float& hi_as_float, float& lo_scaled) {
+    const __half h = __float2half_rn(x);
+    hi_as_float = __half2float(h);
+    lo_scaled = (x - hi_as_float) * kF16LoScale;
+}
+
+// two values at once: hi pair and scaled-residual pair as packed half2 words
+__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi2, uint32_t& lo2) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((x - hf.x) * kF16LoScale, (y - hf.y) * kF16LoScale);
+    hi2 = *reinterpret_cast<const uint32_t*>(&h);
+    lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+}  // namespace tc

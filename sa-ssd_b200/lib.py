@@ -16,6 +16,11 @@ class VoxelParams(ctypes.Structure):
                 ("max_points", ctypes.c_int32), ("max_voxels", ctypes.c_int32)]
 
 
+class Conv2dDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "H", "W", "cin", "cin_stored", "cout", "taps", "relu",
+                                              "out_f32_stride", "out_split_ch")]
+
+
 class GConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("mode", "precision", "cin", "cout", "taps", "in_stride", "out_stride",
                                               "rows_cap", "batch", "H", "W", "relu")]
@@ -46,6 +51,8 @@ _SIGNATURES = {
     "sassd_gconv": (c_int, [ctypes.POINTER(GConvDesc), P, P, P, P, P, P, P, P]),
     "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_gconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "sassd_conv2d_f16x3": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P]),
+    "sassd_sparse_to_bev_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, c_int, P,

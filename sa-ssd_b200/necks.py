@@ -124,8 +124,14 @@ def pack_conv2d_weight(w, dc_order=None):
     return p.contiguous().float()
 
 
-def conv2d_nhwc(x, weight_packed, scale, shift, relu, cout, precision=ops.PREC_FP32, out=None):
-    """x [B,H,W,Cin] NHWC contiguous -> [B,H,W,cout_stride]; 3x3 (pad 1) when taps == 9, 1x1 when 1."""
+def conv2d_nhwc(x, weight_packed, scale, shift, relu, cout, precision=ops.PREC_FP32, out=None, split_out=False):
+    """x [B,H,W,Cin] NHWC contiguous -> [B,H,W,cout_stride]; 3x3 (pad 1) when taps == 9, 1x1 when 1.
+    A ``ops.SplitMap`` input selects the TMA tensor-core kernel (csrc/conv2d_tma.cu); ``split_out`` then keeps
+    the output in split form for the next such layer."""
+    if isinstance(x, ops.SplitMap):
+        sp, f32 = ops.conv2d_split(x, weight_packed, scale, shift, relu, cout, out_split=split_out,
+                                   out_f32=not split_out)
+        return sp if split_out else f32
     B, H, W, cin = x.shape
     taps = weight_packed.shape[0]
     stride = (cout + 3) // 4 * 4
@@ -166,13 +172,15 @@ class BEVNet(nn.Module):
         """x [B,H,W,Cin] (channel order d*C+c when dc_order=(C,D)).  Returns (x, conv6) NHWC."""
         if self.training:
             raise NotImplementedError("sassd_b200 is inference-only: call .eval()")
+        split = isinstance(x, ops.SplitMap)
         for i in range(7):
             scale, shift = fold_bn(getattr(self, "bn%d" % i))
             x = conv2d_nhwc(x, self._weights(i, dc_order if i == 0 else None), scale, shift, True, self.num_filters,
-                            self.precision)
+                            self.precision, split_out=split)
         conv6 = x
         scale, shift = fold_bn(self.bn7)
-        x = conv2d_nhwc(x, self._weights(7, None), scale, shift, True, self.num_filters, self.precision)
+        x = conv2d_nhwc(x, self._weights(7, None), scale, shift, True, self.num_filters, self.precision,
+                        split_out=split)
         return x, conv6
 
     def forward(self, x):
@@ -196,6 +204,7 @@ class SpMiddleFHD(nn.Module):
         self.point_cls = nn.Linear(64, 1, bias=False)
         self.point_reg = nn.Linear(64, 3, bias=False)
         self.row_cap_factor = 4
+        self.dense_tma = True             # F16X3: keep the BEV maps as split fp16 planes and feed the convs by TMA
         self.overlap_rulebooks = True     # build the rulebook chain on a side stream, concurrently with the convs
         self._side = None
 
@@ -219,8 +228,12 @@ class SpMiddleFHD(nn.Module):
             torch.cuda.current_stream().wait_stream(self._side)   # join (also required to end a graph capture)
         C = x._features.shape[1]
         D, H, W = x.spatial_shape
-        bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=x._features.device)
-        ops.sparse_to_bev(x._features, x._indices, x.d_rows, C, D, H, W, bev)
+        if self.fcn.precision == ops.PREC_F16X3 and self.dense_tma:
+            # split fp16 planes + TMA-fed tensor-core convs (conv2d_tma.cu); y / conv6 are ops.SplitMap
+            bev = ops.sparse_to_bev_split(x._features, x._indices, x.d_rows, C, D, H, W, batch_size)
+        else:
+            bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=x._features.device)
+            ops.sparse_to_bev(x._features, x._indices, x.d_rows, C, D, H, W, bev)
         y, conv6 = self.fcn.forward_nhwc(bev, dc_order=(C, D))
         return y, conv6, x
 
@@ -228,4 +241,6 @@ class SpMiddleFHD(nn.Module):
         if not is_test:
             raise NotImplementedError("the auxiliary training branch (cmn.py:121-135) is out of scope")
         y, conv6, x = self.forward_nhwc(voxel_features, coors, batch_size, d_rows, status)
+        if isinstance(y, ops.SplitMap):
+            y, conv6 = y.float(), conv6.float()
         return y.permute(0, 3, 1, 2), conv6.permute(0, 3, 1, 2)

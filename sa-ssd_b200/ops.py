@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import lib as _lib
+from .lib import Conv2dDesc  # noqa: E402
 from .lib import (GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_F16X3, PREC_FP32, PREC_TF32X3, GConvDesc, VoxelParams,
                   check)
 
@@ -46,7 +47,7 @@ def next_pow2(n):
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
             "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
-            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_conv2d_f16x3": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
 LAUNCHES = 0          # running count of kernels launched through this module
@@ -309,3 +310,66 @@ def boxes_iou_bev(a, b):
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
     _call("sassd_boxes_iou_bev", None, _ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------- TMA dense conv on split maps
+class SplitMap:
+    """Activation map as two fp16 planes [2, B, H, W, C_stored] (hi, lo*2048) — the operand format of
+    sassd_conv2d_f16x3; ``channels`` of the C_stored are meaningful, the rest are zero."""
+
+    def __init__(self, planes, channels):
+        self.planes, self.channels = planes, channels
+
+    @property
+    def shape(self):
+        return (self.planes.shape[1], self.planes.shape[2], self.planes.shape[3], self.channels)
+
+    @property
+    def device(self):
+        return self.planes.device
+
+    def float(self):
+        """fp32 NHWC reconstruction (hi + lo/2048), for API-compat consumers and tests."""
+        return (self.planes[0].float() + self.planes[1].float() * (1.0 / 2048.0))[..., : self.channels].contiguous()
+
+    @staticmethod
+    def from_float(x):
+        """Test / compat helper: split an fp32 NHWC map with the same arithmetic as the kernels."""
+        B, H, W, C = x.shape
+        cs = (C + 63) // 64 * 64
+        hi = x.half()
+        lo = ((x - hi.float()) * 2048.0).half()
+        planes = torch.zeros((2, B, H, W, cs), dtype=torch.float16, device=x.device)
+        planes[0, ..., :C] = hi
+        planes[1, ..., :C] = lo
+        return SplitMap(planes, C)
+
+
+def sparse_to_bev_split(feat, coors, d_rows, C, D, H, W, batch):
+    planes = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=feat.device)
+    _call("sassd_sparse_to_bev_split", None, _ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, batch,
+          _ptr(planes), _stream())
+    return SplitMap(planes, D * C)
+
+
+def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=False):
+    """x: SplitMap; weight [taps, cin, cout] fp32 (packed on first use).  Returns (SplitMap | None, fp32 map | None)."""
+    B, H, W, cin = x.shape
+    taps = weight.shape[0]
+    wp = tc_pack_cached(weight, PREC_F16X3)
+    d = Conv2dDesc()
+    d.batch, d.H, d.W, d.cin, d.cin_stored = B, H, W, cin, x.planes.shape[-1]
+    d.cout, d.taps, d.relu = cout, taps, 1 if relu else 0
+    osp = of = None
+    if out_split:
+        cs = (cout + 63) // 64 * 64
+        osp = torch.empty((2, B, H, W, cs), dtype=torch.float16, device=x.device)
+        d.out_split_ch = cs
+    if out_f32:
+        stride = (cout + 3) // 4 * 4
+        of = torch.empty((B, H, W, stride), dtype=torch.float32, device=x.device)
+        d.out_f32_stride = stride
+    label = "conv2d_tma[taps=%d %d->%d]" % (taps, cin, cout)
+    _call("sassd_conv2d_f16x3", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
+          _ptr(osp), _stream())
+    return (SplitMap(osp, cout) if osp is not None else None), of

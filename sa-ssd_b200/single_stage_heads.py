@@ -196,7 +196,7 @@ class PSWarpHead(nn.Module):
         w0, w1 = self._weights()
         scale, shift = fold_bn(self.convs[1])
         c = self.convs[0].out_channels
-        y = conv2d_nhwc(x, w0, scale, shift, True, c, self.precision)
+        y = conv2d_nhwc(x, w0, scale, shift, True, c, self.precision, split_out=isinstance(x, ops.SplitMap))
         return conv2d_nhwc(y, w1, None, None, False, c, self.precision)
 
     def forward_device(self, conv6_nhwc, boxes, d_k):

@@ -369,6 +369,11 @@ def test_rescore_nms_lists(dev):
 
 
 # ------------------------------------------------------------------ whole path
+def _nhwc(t):
+    """aux maps are fp32 NHWC tensors or ops.SplitMap (TMA tensor-core path)."""
+    return t.float() if hasattr(t, "planes") else t
+
+
 def _compare_frame(got, exp, tag, box_atol=1e-4, score_atol=1e-4):
     if exp[0] is None:
         assert got["boxes_lidar"] is None, tag
@@ -403,7 +408,7 @@ def test_end_to_end_points_to_detections(dev, car_model, seeds):
         assert np.array_equal(aux["coors"][fr[b]:fr[b + 1], 1:].cpu().numpy(), st["coors"][b])
         assert np.array_equal(aux["mask"][b].bool().cpu().numpy(), st["anchors_mask"][b])
     assert np.array_equal(aux["sparse"].indices.cpu().numpy(), st["coors3"])
-    x = aux["x"].permute(0, 3, 1, 2).cpu().numpy()
+    x = _nhwc(aux["x"]).permute(0, 3, 1, 2).cpu().numpy()
     ks = aux["d_k"].cpu().numpy()
     total = 0
     for b in range(2):
@@ -458,7 +463,7 @@ def test_end_to_end_tensor_core_path(dev, seeds, prec):
     st = {}
     exp = O.forward_test(sd, clouds, ORACLE_CFG, stages=st)
     assert np.array_equal(aux["sparse"].indices.cpu().numpy(), st["coors3"])
-    x = aux["x"].permute(0, 3, 1, 2).cpu().numpy()
+    x = _nhwc(aux["x"]).permute(0, 3, 1, 2).cpu().numpy()
     total = 0
     for b in range(2):
         sx = max(1.0, float(st["x"][b].abs().max()))

@@ -106,4 +106,56 @@ if stage in ("table", "all"):
 if stage in ("perf", "all"):
     run(ops.GCONV_CONV2D, 200 * 176, 256, 256, 9, True, H=200, W=176, B=1, tag="BEV 3x3 256->256 B=1", time_it=True)
     run(ops.GCONV_CONV2D, 4 * 200 * 176, 256, 256, 9, True, H=200, W=176, B=4, tag="BEV 3x3 256->256 B=4", time_it=True)
+
+
+def run_tma(B, H, W, cin, cout, taps, relu, tag, time_it=False):
+    x = torch.randn(B, H, W, cin, device=dev)
+    w = torch.randn(taps, cin, cout, device=dev) * 0.05
+    scale = torch.rand(cout, device=dev) + 0.5
+    shift = torch.randn(cout, device=dev) * 0.1
+    xs = ops.SplitMap.from_float(x)
+    sp, f32 = ops.conv2d_split(xs, w, scale, shift, relu, cout, out_split=True, out_f32=True)
+    torch.cuda.synchronize()
+    img = x.double().cpu().permute(0, 3, 1, 2)
+    k = 3 if taps == 9 else 1
+    wk = w.double().cpu().view(k, k, cin, cout).permute(3, 2, 0, 1)
+    ref = torch.nn.functional.conv2d(img, wk, padding=k // 2).permute(0, 2, 3, 1)
+    ref = ref * scale.double().cpu() + shift.double().cpu()
+    if relu:
+        ref = ref.clamp_min(0)
+    sc = ref.abs().max().item()
+    e1 = (f32[..., :cout].double().cpu() - ref).abs().max().item()
+    e2 = (sp.float().double().cpu() - ref).abs().max().item()
+    ok = e1 < 2e-5 * max(sc, 1) and e2 < 2e-5 * max(sc, 1)
+    print("%-30s B=%d %dx%d cin=%-3d cout=%-3d taps=%d |ref|max %.3g  err f32-out %.2e  err split-out %.2e  %s" %
+          (tag, B, H, W, cin, cout, taps, sc, e1, e2, "OK" if ok else "MISMATCH"), flush=True)
+    if not ok:
+        d = (f32[..., :cout].double().cpu() - ref).abs()
+        bad = torch.nonzero(d > 1e-3 * max(sc, 1))
+        print("   n_bad", bad.shape[0], "first", bad[:6].tolist())
+        print("   got", f32[0, 0, 0, :6].tolist(), "ref", ref[0, 0, 0, :6].tolist())
+    if time_it:
+        for _ in range(2):
+            ops.conv2d_split(xs, w, scale, shift, relu, cout, out_split=True, out_f32=False)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1_ = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.conv2d_split(xs, w, scale, shift, relu, cout, out_split=True, out_f32=False)
+        e1_.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1_) / 5
+        print("   tma f16x3 %.3f ms  %.1f TFLOP/s (algorithmic fp32)" % (ms, 2.0 * B * H * W * cin * cout * taps / ms / 1e9), flush=True)
+
+
+if stage in ("tma", "all"):
+    run_tma(1, 8, 16, 64, 32, 1, False, "tma 1 tile 1x1")
+    run_tma(1, 8, 16, 64, 32, 9, True, "tma 1 tile 3x3")
+    run_tma(2, 24, 20, 256, 256, 9, True, "tma 256->256 partial tiles")
+    run_tma(1, 40, 36, 320, 256, 9, True, "tma 320->256")
+    run_tma(1, 40, 36, 256, 28, 9, True, "tma 256->28")
+    run_tma(1, 40, 36, 28, 28, 1, False, "tma 28->28 1x1")
+    run_tma(1, 40, 36, 256, 20, 1, False, "tma 256->20 1x1")
+if stage in ("tmaperf", "all"):
+    run_tma(1, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=1", time_it=True)
+    run_tma(4, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=4", time_it=True)
 print("done")
