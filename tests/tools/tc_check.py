@@ -159,3 +159,10 @@ if stage in ("tmaperf", "all"):
     run_tma(1, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=1", time_it=True)
     run_tma(4, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=4", time_it=True)
 print("done")
+if stage in ("tmafull",):
+    run_tma(1, 200, 176, 256, 28, 9, True, "tma full 256->28")
+    run_tma(1, 200, 176, 28, 28, 1, False, "tma full 28->28 1x1")
+    run_tma(1, 200, 176, 256, 20, 1, False, "tma full 256->20 1x1")
+    run_tma(2, 200, 176, 256, 20, 1, False, "tma full B=2 256->20 1x1")
+    run_tma(1, 200, 176, 256, 64, 9, True, "tma full 256->64")
+    run_tma(1, 200, 176, 256, 128, 9, True, "tma full 256->128")
