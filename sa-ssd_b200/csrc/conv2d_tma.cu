@@ -77,7 +77,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const Conv2dArgs p) 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS); }
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
     }
@@ -216,7 +216,8 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const Conv2dArgs p) 
                 }
             }
             tc_fence_before();
-            mbar_arrive(tmem_empty(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(acc));
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
     }

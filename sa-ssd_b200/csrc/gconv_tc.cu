@@ -96,14 +96,14 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_a(s), NUM_PROD_WARPS * 32);
+            mbar_init(full_a(s), NUM_PROD_WARPS);   // one elected arrive per producer warp
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), CL);      // one tcgen05.commit per CTA of the cluster (weight slices)
             mbar_init(empty_a(s), 1);     // this CTA's own commit (A tiles are private)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), NUM_EPI_WARPS * 32);
+            mbar_init(tmem_empty(a), NUM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -133,69 +133,84 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
             const int m = tile * BM + r;
             int x = 0, y = 0;
             if (MODE == SASSD_GCONV_CONV2D) { x = m % W; y = (m / W) % H; }
-            // software pipeline: the global loads of chunk i+1 are in flight while chunk i waits for its
-            // stage, is split and stored (one L2 round trip per chunk would otherwise serialise the producer)
-            int t = 0, kc = 0;
-            int src = rowmap(m, 0, x, y);
-            int src_nt = taps > 1 ? rowmap(m, 1, x, y) : -1;      // row index of the next tap, fetched one tap ahead
+            // software pipeline: the global loads of the next PF chunks are in flight (register ring) while
+            // the current chunk is split, waits for its stage and is stored — the gather is latency-bound
+            // (random rows out of L2), so bytes in flight are what buys throughput
             constexpr int NF4H = PR::NF4 / 2;             // float4 loads per thread per chunk
-            float4 vn[NF4H];
-            auto fetch = [&](int s_row, int kchunk) {
-                const float* rowp = in + (size_t)(s_row < 0 ? 0 : s_row) * in_stride;
+            constexpr int PF = PREC == 0 ? 3 : 2;         // prefetch distance in chunks
+            float4 ring[PF][NF4H];
+            bool ring_live[PF];                           // false = the slot stands for a missing neighbour (zeros)
+            int f_t = 0, f_kc = 0;                        // fetch cursor (tap, channel chunk)
+            int f_src = rowmap(m, 0, x, y);
+            int f_src_nt = taps > 1 ? rowmap(m, 1, x, y) : -1;   // row index one tap ahead of the cursor
+            auto fetch = [&](float4 (&dst)[NF4H], bool& live) {
+                const float* rowp = in + (size_t)(f_src < 0 ? 0 : f_src) * in_stride;
+                live = f_src >= 0;
 #pragma unroll
                 for (int c = 0; c < NF4H; ++c) {
-                    const int k = kchunk * PR::BKC + (hf * NF4H + c) * 4;
-                    vn[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s_row >= 0 && k < cin) vn[c] = __ldg((const float4*)(rowp + k));
+                    const int k = f_kc * PR::BKC + (hf * NF4H + c) * 4;
+                    dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && k < cin) dst[c] = __ldg((const float4*)(rowp + k));
+                }
+                if (++f_kc == kchunks) {
+                    f_kc = 0;
+                    ++f_t;
+                    f_src = f_src_nt;
+                    f_src_nt = (f_t + 1 < taps) ? rowmap(m, f_t + 1, x, y) : -1;
                 }
             };
-            fetch(src, 0);
-            for (int ch = 0; ch < nchunks; ++ch) {
-                // split this chunk (consumes vn), then put the next chunk's loads in flight, then wait/store
-                uint4 ph[4], pl[4];       // this thread's 4 of the 8 16-byte chunks of the hi / lo rows
-                if constexpr (PREC == 0) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (u < nchunks) fetch(ring[u], ring_live[u]);
+            for (int ch0 = 0; ch0 < nchunks; ch0 += PF) {
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int ch = ch0 + u;
+                    if (ch >= nchunks) break;
+                    float4 (&vn)[NF4H] = ring[u];
+                    uint4 ph[4], pl[4];       // this thread's 4 of the 8 16-byte chunks of the hi / lo rows
+                    if (!ring_live[u]) {      // missing neighbour (65 % of the sparse (row, offset) slots): no split math
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { ph[c] = make_uint4(0u, 0u, 0u, 0u); pl[c] = ph[c]; }
+                    } else if constexpr (PREC == 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float4 hi, lo;
+                            split_tf32(vn[c].x, hi.x, lo.x);
+                            split_tf32(vn[c].y, hi.y, lo.y);
+                            split_tf32(vn[c].z, hi.z, lo.z);
+                            split_tf32(vn[c].w, hi.w, lo.w);
+                            ph[c] = *reinterpret_cast<const uint4*>(&hi);
+                            pl[c] = *reinterpret_cast<const uint4*>(&lo);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {      // 8 channels (two float4) -> one 16-byte chunk of halfs
+                            const float4 a = vn[2 * c], b = vn[2 * c + 1];
+                            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                            split_f16x2(a.x, a.y, h0, l0);
+                            split_f16x2(a.z, a.w, h1, l1);
+                            split_f16x2(b.x, b.y, h2, l2);
+                            split_f16x2(b.z, b.w, h3, l3);
+                            ph[c] = make_uint4(h0, h1, h2, h3);
+                            pl[c] = make_uint4(l0, l1, l2, l3);
+                        }
+                    }
+                    if (ch + PF < nchunks) fetch(vn, ring_live[u]);        // refill this ring slot
+                    mbar_wait(empty_a(stage), phase ^ 1u);
+                    uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
+                    uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        float4 hi, lo;
-                        split_tf32(vn[c].x, hi.x, lo.x);
-                        split_tf32(vn[c].y, hi.y, lo.y);
-                        split_tf32(vn[c].z, hi.z, lo.z);
-                        split_tf32(vn[c].w, hi.w, lo.w);
-                        ph[c] = *reinterpret_cast<const uint4*>(&hi);
-                        pl[c] = *reinterpret_cast<const uint4*>(&lo);
+                        const uint32_t off = row_off + (((uint32_t)(hf * 4 + c) ^ sw) << 4);
+                        *(uint4*)(a_hi + off) = ph[c];
+                        *(uint4*)(a_lo + off) = pl[c];
                     }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {      // 8 channels (two float4) -> one 16-byte chunk of halfs
-                        const float4 a = vn[2 * c], b = vn[2 * c + 1];
-                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_f16x2(a.x, a.y, h0, l0);
-                        split_f16x2(a.z, a.w, h1, l1);
-                        split_f16x2(b.x, b.y, h2, l2);
-                        split_f16x2(b.z, b.w, h3, l3);
-                        ph[c] = make_uint4(h0, h1, h2, h3);
-                        pl[c] = make_uint4(l0, l1, l2, l3);
-                    }
+                    fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();               // all 32 lanes fenced; one arrive per warp (256 arrivals on one
+                    if (lane == 0) mbar_arrive(full_a(stage));   // mbarrier per chunk serialise for ~1-2k cycles)
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (++kc == kchunks) {
-                    kc = 0;
-                    ++t;
-                    src = src_nt;
-                    if (t + 1 < taps) src_nt = rowmap(m, t + 1, x, y);
-                }
-                if (ch + 1 < nchunks) fetch(src, kc);
-                mbar_wait(empty_a(stage), phase ^ 1u);
-                uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
-                uint8_t* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t off = row_off + (((uint32_t)(hf * 4 + c) ^ sw) << 4);
-                    *(uint4*)(a_hi + off) = ph[c];
-                    *(uint4*)(a_lo + off) = pl[c];
-                }
-                fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(full_a(stage));
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == WARP_BLOAD) {
@@ -305,7 +320,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                 }
             }
             tc_fence_before();
-            mbar_arrive(tmem_empty(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(acc));
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
     }
