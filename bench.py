@@ -306,9 +306,11 @@ def run_ours(args, rank, world, local):
                                        (2.0 if args.precision in ("tf32x3", "mixed") else 1.0),
                         share_of_step=bev["ms_total_per_step"] / sum(v["ms_total_per_step"] for v in prof.values()))
     sp_bytes, sp_flops, pairs = algorithmic_work(aux, B)
-    sp_ms = sum(v["ms_total_per_step"] for k, v in prof.items() if k.startswith("gconv[table"))
+    sp_ms = sum(v["ms_total_per_step"] for k, v in prof.items() if k.startswith("gconv[table") or k.startswith("spconv_split[taps=27"))
     sp_kernel = {"fp32": "gconv_ffma_kernel<TABLE,...>", "mixed": "gconv_ffma_kernel<TABLE,...>"}.get(
         args.precision, "tc::gconv_tc_kernel<TABLE,BN,1,%s>" % args.precision.upper())
+    if any(k.startswith("spconv_split") for k in prof):
+        sp_kernel = "sps::spconv_split_kernel<TABLE,BN> (cp.async gather of split fp16 rows, tcgen05 FP16x3)"
     sp_ach = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
     roofline_sparse = dict(kernel=sp_kernel + " x13 ruled sparse convs", bound="hbm", achieved=sp_ach,
                            peak=peaks["hbm_gbs"], unit="GB/s", frac=sp_ach / peaks["hbm_gbs"], traffic=None,
@@ -354,7 +356,7 @@ def run_ours(args, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

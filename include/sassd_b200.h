@@ -176,6 +176,25 @@ int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split,
 int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
                               int D, int H, int W, int batch, void* bev_split, sassd_stream_t stream);
 
+/* Ruled sparse conv on "split rows" (two fp16 planes [2][rows][C], C % 8 == 0; hi = half(x), lo = half((x-hi)*2048)):
+ * same semantics as sassd_gconv TABLE / ROWS mode with SASSD_PREC_F16X3, but the gather is 16-byte cp.async copies
+ * straight into the tensor-core operand tiles and the epilogue writes the next layer's planes (out_split, out_ch
+ * channels, zero beyond cout) and/or fp32 rows.  taps == 1: row(m) = m.  cout <= 64. */
+typedef struct {
+    int32_t cin, cout, taps;         /* cin = stored channels of the input planes */
+    int32_t rows_cap, in_rows_cap;   /* output rows capacity; rows of the input planes (plane stride) */
+    int32_t relu, out_ch, out_f32_stride;
+} sassd_spconv_desc;
+int sassd_spconv_f16x3(const sassd_spconv_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
+                       const float* shift, const int32_t* nbr, const int32_t* d_rows, void* out_split, float* out_f32,
+                       sassd_stream_t stream);
+/* fp32 rows [rows, cin] -> split rows [2][rows_cap][cs] (cs >= cin, cs % 8 == 0, padding zero). */
+int sassd_features_to_split(const float* feat, const int32_t* d_rows, int rows_cap, int cin, int cs, void* out_split,
+                            sassd_stream_t stream);
+/* dense() of split rows into a (pre-zeroed) split BEV map [2,batch,H,W,D*C]. */
+int sassd_split_rows_to_bev(const void* feat_split, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
+                            int D, int H, int W, int batch, void* bev_split, sassd_stream_t stream);
+
 /* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
  * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;
  * the permutation is folded into the first BEV conv's weights).  The map must be

@@ -21,6 +21,11 @@ class Conv2dDesc(ctypes.Structure):
                                               "out_f32_stride", "out_split_ch")]
 
 
+class SpconvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("cin", "cout", "taps", "rows_cap", "in_rows_cap", "relu", "out_ch",
+                                              "out_f32_stride")]
+
+
 class GConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("mode", "precision", "cin", "cout", "taps", "in_stride", "out_stride",
                                               "rows_cap", "batch", "H", "W", "relu")]
@@ -52,6 +57,9 @@ _SIGNATURES = {
     "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_gconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "sassd_conv2d_f16x3": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P]),
+    "sassd_spconv_f16x3": (c_int, [ctypes.POINTER(SpconvDesc), P, P, P, P, P, P, P, P, P]),
+    "sassd_features_to_split": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "sassd_split_rows_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_sparse_to_bev_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),

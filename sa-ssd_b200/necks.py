@@ -91,7 +91,7 @@ class VxNet(nn.Module):
         feature convolutions, which wait on each rulebook's event when they first use it."""
         main = torch.cuda.current_stream()
         side_stream.wait_stream(main)
-        dev = x._features.device
+        dev = x.device
         with torch.cuda.stream(side_stream):
             coors, d_rows, shape, cap = x._indices, x.d_rows, x.spatial_shape, x.rows_cap
             index = ops.hash_build(ops.HashIndex(cap, dev), coors, d_rows, x.batch_size, shape, x.status)
@@ -221,19 +221,23 @@ class SpMiddleFHD(nn.Module):
         x.row_cap_factor = self.row_cap_factor
         if self.overlap_rulebooks:
             if self._side is None:
-                self._side = torch.cuda.Stream(device=x._features.device)
+                self._side = torch.cuda.Stream(device=x.device)
             self.backbone.prebuild_rulebooks(x, self._side)
         x, middle = self.backbone(x)
         if self.overlap_rulebooks:
             torch.cuda.current_stream().wait_stream(self._side)   # join (also required to end a graph capture)
-        C = x._features.shape[1]
+        C = x._channels
         D, H, W = x.spatial_shape
         if self.fcn.precision == ops.PREC_F16X3 and self.dense_tma:
             # split fp16 planes + TMA-fed tensor-core convs (conv2d_tma.cu); y / conv6 are ops.SplitMap
-            bev = ops.sparse_to_bev_split(x._features, x._indices, x.d_rows, C, D, H, W, batch_size)
+            if x._split is not None and x._split.shape[2] == C:
+                bev = ops.split_rows_to_bev(x._split, x._indices, x.d_rows, C, D, H, W, batch_size)
+            else:
+                bev = ops.sparse_to_bev_split(x.features_cap(), x._indices, x.d_rows, C, D, H, W, batch_size)
         else:
-            bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=x._features.device)
-            ops.sparse_to_bev(x._features, x._indices, x.d_rows, C, D, H, W, bev)
+            feats = x.features_cap()
+            bev = torch.zeros((batch_size, H, W, D * C), dtype=torch.float32, device=feats.device)
+            ops.sparse_to_bev(feats, x._indices, x.d_rows, C, D, H, W, bev)
         y, conv6 = self.fcn.forward_nhwc(bev, dc_order=(C, D))
         return y, conv6, x
 

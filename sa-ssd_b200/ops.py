@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import lib as _lib
-from .lib import Conv2dDesc  # noqa: E402
+from .lib import Conv2dDesc, SpconvDesc  # noqa: E402
 from .lib import (GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_F16X3, PREC_FP32, PREC_TF32X3, GConvDesc, VoxelParams,
                   check)
 
@@ -47,7 +47,7 @@ def next_pow2(n):
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
             "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
-            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_conv2d_f16x3": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_conv2d_f16x3": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
 LAUNCHES = 0          # running count of kernels launched through this module
@@ -375,3 +375,45 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     _call("sassd_conv2d_f16x3", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
           _ptr(osp), _stream())
     return (SplitMap(osp, cout) if osp is not None else None), of
+
+
+# ---------------------------------------------------------------------------- sparse conv on split rows
+def features_to_split(feat, d_rows=None):
+    """fp32 rows [cap, C] -> split rows [2, cap, cs] fp16 (cs = C rounded up to 8)."""
+    cap, C = feat.shape
+    cs = (C + 7) // 8 * 8
+    out = torch.empty((2, cap, cs), dtype=torch.float16, device=feat.device)
+    _call("sassd_features_to_split", None, _ptr(feat), _ptr(d_rows), cap, C, cs, _ptr(out), _stream())
+    return out
+
+
+def split_rows_float(planes, channels):
+    """fp32 reconstruction of split rows (API-compat consumers and tests)."""
+    return (planes[0].float() + planes[1].float() * (1.0 / 2048.0))[:, :channels].contiguous()
+
+
+def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d_rows=None, want_f32=False):
+    """planes [2, in_cap, cin_stored] fp16; weight [taps, cin, cout] fp32 (packed on first use).
+    Returns (out planes [2, rows_cap, out_ch], fp32 rows or None)."""
+    taps = weight.shape[0]
+    wp = tc_pack_cached(weight, PREC_F16X3)
+    d = SpconvDesc()
+    d.cin, d.cout, d.taps = planes.shape[2], cout, taps
+    d.rows_cap, d.in_rows_cap, d.relu = rows_cap, planes.shape[1], 1 if relu else 0
+    d.out_ch = (cout + 7) // 8 * 8
+    out = torch.empty((2, rows_cap, d.out_ch), dtype=torch.float16, device=planes.device)
+    of = None
+    if want_f32:
+        d.out_f32_stride = (cout + 3) // 4 * 4
+        of = torch.empty((rows_cap, d.out_f32_stride), dtype=torch.float32, device=planes.device)
+    label = "spconv_split[taps=%d %d->%d]" % (taps, weight.shape[1], cout)
+    _call("sassd_spconv_f16x3", label, ctypes.byref(d), _ptr(planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(nbr),
+          _ptr(d_rows), _ptr(out), _ptr(of), _stream())
+    return out, of
+
+
+def split_rows_to_bev(planes, coors, d_rows, C, D, H, W, batch):
+    bev = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=planes.device)
+    _call("sassd_split_rows_to_bev", None, _ptr(planes), _ptr(coors), _ptr(d_rows), planes.shape[1], C, D, H, W, batch,
+          _ptr(bev), _stream())
+    return SplitMap(bev, D * C)

@@ -16,6 +16,9 @@ from torch import nn
 from . import ops
 
 
+SPLIT_ROWS = True   # F16X3 sparse layers keep their features as split fp16 rows (spconv_split.cu)
+
+
 class Rulebook:
     """nbr [rows_cap, 27] + the output coordinate set of one indice_key."""
 
@@ -44,6 +47,8 @@ class SparseConvTensor:
         self.indice_dict = {}
         self._index = None  # hash index over self._indices
         self.row_cap_factor = 8
+        self._split = None  # fp16 hi/lo planes [2, cap, C8] when the layer chain runs in split form
+        self._channels = self._features.shape[1]
 
     # exact-shape views (synchronise)
     def num_rows(self):
@@ -51,7 +56,20 @@ class SparseConvTensor:
 
     @property
     def features(self):
+        if self._features is None:      # split-row chain: reconstruct fp32 (hi + lo/2048) for API-compat consumers
+            return ops.split_rows_float(self._split, self._channels)[: self.num_rows()]
         return self._features[: self.num_rows()]
+
+    def features_cap(self):
+        """capacity-sized fp32 feature matrix (no sync)."""
+        if self._features is None:
+            return ops.split_rows_float(self._split, self._channels)
+        return self._features
+
+    def split_planes(self):
+        if self._split is None:
+            self._split = ops.features_to_split(self._features, self.d_rows)
+        return self._split
 
     @property
     def indices(self):
@@ -59,17 +77,23 @@ class SparseConvTensor:
 
     @property
     def rows_cap(self):
-        return self._features.shape[0]
+        return self._features.shape[0] if self._features is not None else self._split.shape[1]
+
+    @property
+    def device(self):
+        return self._indices.device
 
     def hash_index(self):
         if self._index is None:
-            self._index = ops.hash_build(ops.HashIndex(self.rows_cap, self._features.device), self._indices,
+            self._index = ops.hash_build(ops.HashIndex(self.rows_cap, self.device), self._indices,
                                          self.d_rows, self.batch_size, self.spatial_shape, self.status)
         return self._index
 
-    def _derive(self, features, indices=None, spatial_shape=None, d_rows=None, index=None):
+    def _derive(self, features, indices=None, spatial_shape=None, d_rows=None, index=None, split=None, channels=None):
         t = SparseConvTensor.__new__(SparseConvTensor)
         t._features = features
+        t._split = split
+        t._channels = channels if channels is not None else (features.shape[1] if features is not None else None)
         t._indices = self._indices if indices is None else indices
         t.spatial_shape = self.spatial_shape if spatial_shape is None else spatial_shape
         t.batch_size = self.batch_size
@@ -82,10 +106,11 @@ class SparseConvTensor:
 
     def dense(self):
         """[B, C, D, H, W] like spconv's scatter_nd + permute (cmn.py:112)."""
-        C = self._features.shape[1]
+        feats = self._features if self._features is not None else ops.split_rows_float(self._split, self._channels)
+        C = feats.shape[1]
         D, H, W = self.spatial_shape
-        bev = torch.zeros((self.batch_size, H, W, D * C), dtype=torch.float32, device=self._features.device)
-        ops.sparse_to_bev(self._features, self._indices, self.d_rows, C, D, H, W, bev)
+        bev = torch.zeros((self.batch_size, H, W, D * C), dtype=torch.float32, device=feats.device)
+        ops.sparse_to_bev(feats, self._indices, self.d_rows, C, D, H, W, bev)
         # internal NHWC (d, c) order -> reference [B, C, D, H, W]
         return bev.view(self.batch_size, H, W, D, C).permute(0, 4, 3, 1, 2).contiguous()
 
@@ -141,6 +166,22 @@ class _SparseConvBase(nn.Module):
         wp = w.detach().reshape(taps, self.in_channels, self.out_channels).contiguous()
         if shift is None and self.bias is not None:
             shift = self.bias.detach()
+        if self.precision == ops.PREC_F16X3 and SPLIT_ROWS and self.out_channels <= 64:
+            # split-row chain: cp.async-fed tensor-core kernel (csrc/spconv_split.cu), output stays split
+            planes = x.split_planes()
+            if taps == 1:
+                out, _ = ops.spconv_split(planes, wp, scale, shift, relu, self.out_channels, x.rows_cap,
+                                          d_rows=x.d_rows)
+                return x._derive(None, split=out, channels=self.out_channels)
+            rb = self._rulebook(x)
+            out, _ = ops.spconv_split(planes, wp, scale, shift, relu, self.out_channels, rb.nbr.shape[0], nbr=rb.nbr,
+                                      d_rows=rb.d_rows_out)
+            if self.subm:
+                return x._derive(None, split=out, channels=self.out_channels)
+            return x._derive(None, indices=rb.coors_out, spatial_shape=rb.shape_out, d_rows=rb.d_rows_out,
+                             index=rb.index_out, split=out, channels=self.out_channels)
+        if x._features is None:
+            x = x._derive(ops.split_rows_float(x._split, x._channels))
         if taps == 1:
             out = torch.empty((x.rows_cap, self.out_channels), dtype=torch.float32, device=wp.device)
             ops.gconv(x._features, wp, scale, shift, out, mode=ops.GCONV_ROWS, taps=1, cin=self.in_channels,
@@ -207,6 +248,7 @@ class SparseSequential(nn.Sequential):
                     continue
                 x = m(x)
             else:
-                x = x._derive(m(x._features))
+                feats = x._features if x._features is not None else ops.split_rows_float(x._split, x._channels)
+                x = x._derive(m(feats))
             i += 1
         return x

@@ -166,3 +166,54 @@ if stage in ("tmafull",):
     run_tma(2, 200, 176, 256, 20, 1, False, "tma full B=2 256->20 1x1")
     run_tma(1, 200, 176, 256, 64, 9, True, "tma full 256->64")
     run_tma(1, 200, 176, 256, 128, 9, True, "tma full 256->128")
+
+
+def run_split(M, cin, cout, taps, relu, tag, density=0.3):
+    rs = np.random.RandomState(cin * 100 + cout)
+    x = torch.randn(M, cin, device=dev)
+    w = torch.randn(taps, cin, cout, device=dev) * 0.1
+    scale = torch.rand(cout, device=dev) + 0.5
+    shift = torch.randn(cout, device=dev) * 0.1
+    nbr = None
+    if taps > 1:
+        nbr = torch.from_numpy(np.where(rs.rand(M, taps) < density, rs.randint(0, M, (M, taps)), -1).astype(np.int32)).to(dev)
+    d_rows = torch.tensor([M - 5], dtype=torch.int32, device=dev)
+    planes = ops.features_to_split(x)
+    out, of = ops.spconv_split(planes, w, scale, shift, relu, cout, M, nbr=nbr, d_rows=d_rows, want_f32=True)
+    torch.cuda.synchronize()
+    xd, wd = x.double().cpu(), w.double().cpu()
+    ref = torch.zeros(M, cout, dtype=torch.float64)
+    if taps == 1:
+        ref = xd @ wd[0]
+    else:
+        nb = nbr.cpu().long()
+        for t in range(taps):
+            o = torch.nonzero(nb[:, t] >= 0).view(-1)
+            ref.index_add_(0, o, xd[nb[o, t]] @ wd[t])
+    ref = ref * scale.double().cpu() + shift.double().cpu()
+    if relu:
+        ref = ref.clamp_min(0)
+    n = M - 5
+    sc = ref.abs().max().item()
+    e1 = (of[:n, :cout].double().cpu() - ref[:n]).abs().max().item()
+    e2 = (ops.split_rows_float(out, cout)[:n].double().cpu() - ref[:n]).abs().max().item()
+    ok = e1 < 2e-5 * max(sc, 1) and e2 < 2e-5 * max(sc, 1)
+    print("%-26s M=%-6d cin=%-3d cout=%-3d taps=%-2d |ref|max %.3g  err f32 %.2e  err split %.2e  %s" %
+          (tag, M, cin, cout, taps, sc, e1, e2, "OK" if ok else "MISMATCH"), flush=True)
+    if not ok:
+        d = (of[:n, :cout].double().cpu() - ref[:n]).abs()
+        bad = torch.nonzero(d > 1e-3 * max(sc, 1))
+        print("   n_bad", bad.shape[0], "first", bad[:6].tolist())
+        print("   got", of[0, :6].tolist(), "ref", ref[0, :6].tolist())
+
+
+if stage in ("split",):
+    run_split(128, 8, 16, 1, False, "split rows 1 tile")
+    run_split(300, 4, 16, 27, True, "split table 4->16")
+    run_split(3000, 16, 16, 27, True, "split table 16->16")
+    run_split(3000, 16, 32, 27, True, "split table 16->32")
+    run_split(3000, 32, 64, 27, True, "split table 32->64")
+    run_split(3000, 64, 64, 27, True, "split table 64->64")
+    run_split(20000, 64, 64, 27, True, "split table 64->64 big")
+    run_split(3000, 64, 64, 1, True, "split rows 64->64")
+    print("done split")
