@@ -143,7 +143,7 @@ __device__ __forceinline__ float rotated_iou(const float* box_a, const float* bo
 // mask[(frame*n_cap + i) * colb_cap + cb] bit j <=> iou(i, cb*64+j) > thr ; tiles with cb >= rb only.
 // The grid is fixed (CUDA-graph friendly); each CTA walks the frame's live upper-triangle tiles,
 // whose number depends on the device-side candidate count.
-#define NMS_MASK_THREADS 512   // 64 rows x 8 column groups of 8
+#define NMS_MASK_THREADS 1024   // 64 rows x 16 column groups of 4
 __global__ void __launch_bounds__(NMS_MASK_THREADS)
 nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, int n_fixed, int n_cap, int colb_cap,
                 float thr, unsigned long long* __restrict__ mask) {
@@ -173,7 +173,7 @@ nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, i
             for (int e = 0; e < 5; ++e) cur[e] = bx[(size_t)i * 5 + e];
             unsigned long long bits = 0;
             const int start = (rb == cb) ? r + 1 : 0;
-            const int j0 = max(start, g * 8), j1 = min(col_size, g * 8 + 8);
+            const int j0 = max(start, g * 4), j1 = min(col_size, g * 4 + 4);
             for (int j = j0; j < j1; j++)
                 if (rotated_iou(cur, s_col + j * 5) > thr) bits |= 1ULL << j;
             if (bits) atomicOr(&s_bits[r], bits);

@@ -217,3 +217,26 @@ if stage in ("split",):
     run_split(20000, 64, 64, 27, True, "split table 64->64 big")
     run_split(3000, 64, 64, 1, True, "split rows 64->64")
     print("done split")
+if stage in ("splitperf",):
+    M, cin, cout, taps = 120000, 64, 64, 27
+    rs = np.random.RandomState(1)
+    x = torch.randn(M, cin, device=dev)
+    w = torch.randn(taps, cin, cout, device=dev) * 0.1
+    # spatially coherent-ish neighbours: mostly nearby rows
+    nb = np.where(rs.rand(M, taps) < 0.35, np.clip(np.arange(M)[:, None] + rs.randint(-300, 300, (M, taps)), 0, M - 1), -1).astype(np.int32)
+    nbr = torch.from_numpy(nb).to(dev)
+    d_rows = torch.tensor([M], dtype=torch.int32, device=dev)
+    planes = ops.features_to_split(x)
+    for _ in range(2):
+        ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr, d_rows=d_rows)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr, d_rows=d_rows)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    P = int((nb >= 0).sum())
+    print("splitperf dbg=%s: %.3f ms  pair-model %.0f GB/s  (%.0f clk/chunk/tile)" % (
+        os.environ.get("SASSD_SPS_DBG", "0"), ms, P * (4 * cin + 4 * cout + 8) / ms / 1e6,
+        ms * 1e-3 * 1.9e9 / (27 * (M / 128) / 148)), flush=True)
