@@ -163,7 +163,8 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const Conv2dArgs p) 
             const int y = ty * TILE_H + py, x = tx * TILE_W + px;
             const bool valid = y < p.H && x < p.W;
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
-            mbar_wait(tmem_full(acc), acc_phase);
+            if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
+            __syncwarp();
             tc_fence_after();
             constexpr int CW = (BN >= 32) ? 32 : 16;
 #pragma unroll 1

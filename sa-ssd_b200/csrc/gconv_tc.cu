@@ -197,7 +197,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                         }
                     }
                     if (ch + PF < nchunks) fetch(vn, ring_live[u]);        // refill this ring slot
-                    mbar_wait(empty_a(stage), phase ^ 1u);
+                    if (lane == 0) mbar_wait(empty_a(stage), phase ^ 1u);   // one polling lane per warp
+                    __syncwarp();
                     uint8_t* a_hi = base_ptr + stage * C::STAGE_BYTES;
                     uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
@@ -280,7 +281,8 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            mbar_wait(tmem_full(acc), acc_phase);
+            if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
+            __syncwarp();
             tc_fence_after();
             const int m = tile * BM + r;
             float* orow = out + (size_t)m * out_stride;

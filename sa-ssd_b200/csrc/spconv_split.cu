@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                 if (t + 1 < p.taps) src_next = (m < M) ? __ldg(&p.nbr[(size_t)m * p.taps + t + 1]) : -1;
                 const __half* rowp = p.in + (size_t)(src < 0 ? 0 : src) * p.cin;
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(empty(stage), phase ^ 1u);
+                    // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
+                    // word slow every other barrier operation of the CTA)
+                    if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
+                    __syncwarp();
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -198,7 +201,8 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            mbar_wait(tmem_full(acc), acc_phase);
+            if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
+            __syncwarp();
             tc_fence_after();
             const int m = tile * BM + r;
             constexpr int CW = (BN >= 32) ? 32 : 16;
