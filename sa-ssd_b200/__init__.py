@@ -8,6 +8,7 @@ interface.  Import name: ``sassd_b200`` (alias of the ``sa-ssd_b200/`` directory
 __version__ = "0.1.0"
 
 from .config import Config, obj_from_dict  # noqa: F401
+from .results import Calibration, kitti_bbox2results  # noqa: F401
 
 
 def build_from_config(cfg, device="cuda", data_key="val"):
