@@ -207,9 +207,10 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                         *(uint4*)(a_hi + off) = ph[c];
                         *(uint4*)(a_lo + off) = pl[c];
                     }
-                    fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
-                    __syncwarp();               // all 32 lanes fenced; one arrive per warp (256 arrivals on one
-                    if (lane == 0) mbar_arrive(full_a(stage));   // mbarrier per chunk serialise for ~1-2k cycles)
+                    // no proxy fence here (it lowers to MEMBAR.ALL.CTA and would wait for the prefetch ring's
+                    // loads still in flight); the MMA lane fences after its mbarrier wait
+                    __syncwarp();               // one arrive per warp (256 arrivals on one mbarrier per chunk
+                    if (lane == 0) mbar_arrive(full_a(stage));   // serialise for ~1-2k cycles)
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -253,6 +254,7 @@ gconv_tc_kernel(const float* __restrict__ in, const float* __restrict__ wpack, c
                 const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
                 for (int ch = 0; ch < nchunks; ++ch) {
                     mbar_wait(full_a(stage), phase);
+                    fence_proxy_async();        // producers' generic-proxy stores -> visible to the async proxy
                     mbar_wait(full_b(stage), phase);
                     tc_fence_after();
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;

@@ -9,6 +9,10 @@
 // tiles; no registers are staged and no split math runs in the main loop (the producing layer's epilogue wrote
 // the planes).  cp.async groups give a 3-chunk-deep gather pipeline; completion -> fence.proxy.async -> one
 // mbarrier arrive per warp hands the tile to the MMA lane.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "tc_common.cuh"
 
 namespace sps {
@@ -17,26 +21,29 @@ using namespace tc;
 
 constexpr int BKC = 64;                 // channels per chunk
 constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
-constexpr int THREADS3 = (EPI_WARPS + PROD_WARPS + 2) * 32;   // 448
-constexpr int W_MMA = EPI_WARPS + PROD_WARPS, W_BLOAD = W_MMA + 1;
-constexpr int DEPTH = 3;                // cp.async groups in flight per producer thread
+constexpr int THREADS3 = (EPI_WARPS + PROD_WARPS + 3) * 32;   // 480
+constexpr int W_MMA = EPI_WARPS + PROD_WARPS, W_BLOAD = W_MMA + 1, W_FENCE = W_MMA + 2;
+constexpr int TRACE_CHUNKS = 81;
 
 template <int BN>
 struct Cfg3 {
     static constexpr int B_TILE_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = 4;
-    static constexpr int ACC_BUFS = 2;                                    // BN <= 64: 4*BN <= 512 columns
-    static constexpr int TMEM_COLS = (ACC_BUFS * 2 * BN < 32) ? 32 : ACC_BUFS * 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int ACC_BUFS = 2;
+    // per accumulator buffer: [big | small1] written by the N = 2*BN instruction, then small2
+    static constexpr int ACC_COLS = 3 * BN;
+    static constexpr int TMEM_COLS = ACC_BUFS * ACC_COLS <= 128 ? 128 : (ACC_BUFS * ACC_COLS <= 256 ? 256 : 512);
+    static constexpr int NBR_TILE_BYTES = BM * 27 * 4;                    // one tile's rows of the [rows, 27] table
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * NBR_TILE_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {   // arrive when this thread's prior cp.async land
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 
 struct Args {
     const __half* in;       // [2][in_rows_cap][cin]
@@ -50,6 +57,9 @@ struct Args {
     size_t out_plane;
     float* out_f32;         // [rows_cap][out_f32_stride] or null
     int cin, cout, taps, rows_cap, relu, out_ch, out_f32_stride;
+    long long* trace;       // dbg & 64: per-chunk clock64() stamps of CTA 0 [3 agents][TRACE_CHUNKS][4]
+    int dbg;                // SASSD_SPS_DBG (timing experiments only): 8 = stale weight stages, 16 = no MMAs,
+                            // 32 = no gather copies, 64 = dump CTA 0's timeline, 128 = MMA lane fences itself
 };
 
 template <int TABLE, int BN>
@@ -57,29 +67,38 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     using C = Cfg3<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    auto full_a = [&](int s) { return bar_base + 8u * s; };
-    auto full_b = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    auto empty = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-    auto tmem_full = [&](int a) { return bar_base + 8u * (3 * C::STAGES + a); };
-    auto tmem_empty = [&](int a) { return bar_base + 8u * (3 * C::STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (3 * C::STAGES + 4);
-    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (3 * C::STAGES + 4));
+    const uint32_t nbr_base = base + C::STAGES * C::STAGE_BYTES;
+    const int* nbr_smem = (const int*)(base_ptr + C::STAGES * C::STAGE_BYTES);
+    const uint32_t bar_base = nbr_base + 2 * C::NBR_TILE_BYTES;
+    auto full_a = [&](int s) { return bar_base + 8u * s; };                       // 256 async producer arrivals
+    auto full_b = [&](int s) { return bar_base + 8u * (C::STAGES + s); };         // weight block landed
+    auto ready_a = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };    // full_a + proxy fence done
+    auto empty = [&](int s) { return bar_base + 8u * (3 * C::STAGES + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (4 * C::STAGES + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (4 * C::STAGES + 2 + a); };
+    auto nbr_full = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 4 + b); };
+    auto nbr_empty = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 6 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 8);
+    volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.d_rows ? min(__ldg(p.d_rows), p.rows_cap) : p.rows_cap;
     const int ntiles = (M + BM - 1) / BM;
     const int kchunks = (p.cin + BKC - 1) / BKC;
     const int nchunks = p.taps * kchunks;
+    const bool nbr_tiles = TABLE && p.taps <= 27;
+    const bool helper_fence = !(p.dbg & 128);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_a(s), PROD_WARPS);
+            mbar_init(full_a(s), PROD_WARPS * 32);
             mbar_init(full_b(s), 1);
+            mbar_init(ready_a(s), 1);
             mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(nbr_full(b), 1); mbar_init(nbr_empty(b), PROD_WARPS); }
         fence_barrier_init();
     }
     if (warp == W_MMA) {
@@ -95,100 +114,173 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ===================== A producers: cp.async gather of split rows =====================
+        // Nothing in this instruction stream waits for data: every thread issues its eight 16-byte copies and an
+        // asynchronous mbarrier arrive that fires when they have landed, so the gather runs STAGES chunks ahead.
         const int pt = threadIdx.x - EPI_WARPS * 32;
         const int r = pt & 127, hf = pt >> 7;
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        int stage = 0;                 // stage being issued
+        int stage = 0;
         uint32_t phase = 0;
-        int done_stage = 0;            // oldest stage whose copies are still unsignalled
-        int inflight = 0;              // committed, unsignalled groups
-        auto signal_oldest = [&]() {   // caller guarantees the oldest group has completed (cp.async.wait_group)
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_a(done_stage));
-            if (++done_stage == C::STAGES) done_stage = 0;
-            --inflight;
-        };
+        int nb = 0;                    // neighbour-table buffer of this tile
+        uint32_t nb_phase = 0;
+        int tchunk = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m = tile * BM + r;
-            int src_next = -1;
-            if (m < M) src_next = TABLE ? __ldg(&p.nbr[(size_t)m * p.taps]) : m;
+            // rows of the table the loader thread copied for this tile (whole 16-byte units only)
+            const int rows_here = min(BM, p.rows_cap - tile * BM);
+            const int rows_copied = nbr_tiles ? ((rows_here * p.taps * 4) & ~15) / (p.taps * 4) : 0;
+            const int* nrow = nbr_smem + nb * (C::NBR_TILE_BYTES / 4) + r * p.taps;
+            const bool from_smem = nbr_tiles && r < rows_copied;
+            if (nbr_tiles) {
+                if (lane == 0) mbar_wait(nbr_full(nb), nb_phase);
+                __syncwarp();
+            }
             for (int t = 0; t < p.taps; ++t) {
-                const int src = src_next;
-                if (t + 1 < p.taps) src_next = (m < M) ? __ldg(&p.nbr[(size_t)m * p.taps + t + 1]) : -1;
+                int src = -1;
+                if (m < M) src = TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
                 const __half* rowp = p.in + (size_t)(src < 0 ? 0 : src) * p.cin;
                 for (int kc = 0; kc < kchunks; ++kc) {
+                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && pt == 0 && tchunk < TRACE_CHUNKS;
+                    long long ts0 = 0, ts1 = 0;
+                    if (tr) ts0 = clock64();
                     // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
                     // word slow every other barrier operation of the CTA)
                     if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
                     __syncwarp();
+                    if (tr) ts1 = clock64();
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
+                    if (!(p.dbg & 32)) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int q = hf * 4 + c;                        // 16-byte piece (8 channels) of the row
-                        const int k = kc * BKC + q * 8;
-                        const uint32_t nbytes = (src >= 0 && k < p.cin) ? 16u : 0u;   // 0 -> hardware zero fill
-                        const __half* sp = rowp + (nbytes ? k : 0);
-                        const uint32_t off = ((uint32_t)q ^ sw) << 4;
-                        cp_async16(a_hi + off, sp, nbytes);
-                        cp_async16(a_lo + off, sp + p.in_plane, nbytes);
+                        for (int c = 0; c < 4; ++c) {
+                            const int q = hf * 4 + c;                        // 16-byte piece (8 channels) of the row
+                            const int k = kc * BKC + q * 8;
+                            const uint32_t nbytes = (src >= 0 && k < p.cin) ? 16u : 0u;   // 0 -> hardware zero fill
+                            const __half* sp = rowp + (nbytes ? k : 0);
+                            const uint32_t off = ((uint32_t)q ^ sw) << 4;
+                            cp_async16(a_hi + off, sp, nbytes);
+                            cp_async16(a_lo + off, sp + p.in_plane, nbytes);
+                        }
                     }
-                    cp_async_commit();
-                    ++inflight;
+                    cp_async_arrive_noinc(full_a(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-                    if (inflight == DEPTH) { cp_async_wait<DEPTH - 1>(); signal_oldest(); }
+                    if (tr) {
+                        long long* q = p.trace + (size_t)(0 * TRACE_CHUNKS + tchunk) * 4;
+                        q[0] = ts0; q[1] = ts1; q[2] = clock64(); q[3] = 0;
+                    }
+                    ++tchunk;
+                }
+            }
+            if (nbr_tiles) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(nbr_empty(nb));
+                if (++nb == 2) { nb = 0; nb_phase ^= 1u; }
+            }
+        }
+    } else if (warp == W_BLOAD) {
+        // ===================== weights + neighbour-table tiles (bulk copies) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int nb = 0, issued = 0;
+            uint32_t nb_phase = 0;
+            auto load_nbr = [&](int tile) {     // one bulk copy: the tile's rows of the table are contiguous
+                const int rows_here = min(BM, p.rows_cap - tile * BM);
+                const uint32_t bytes = (uint32_t)(rows_here * p.taps * 4) & ~15u;
+                mbar_wait(nbr_empty(nb), nb_phase ^ 1u);
+                mbar_expect_tx(nbr_full(nb), bytes);
+                if (bytes) bulk_g2s(nbr_base + nb * C::NBR_TILE_BYTES, p.nbr + (size_t)tile * BM * p.taps, bytes, nbr_full(nb));
+                if (++nb == 2) { nb = 0; nb_phase ^= 1u; }
+            };
+            if (nbr_tiles && (int)blockIdx.x < ntiles) load_nbr(blockIdx.x);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (nbr_tiles && tile + (int)gridDim.x < ntiles) load_nbr(tile + gridDim.x);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && issued < TRACE_CHUNKS;
+                    long long ts0 = 0;
+                    if (tr) ts0 = clock64();
+                    mbar_wait(empty(stage), phase ^ 1u);
+                    if (tr) {
+                        long long* q = p.trace + (size_t)(1 * TRACE_CHUNKS + issued) * 4;
+                        q[0] = ts0; q[1] = clock64(); q[2] = 0; q[3] = 0;
+                    }
+                    const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
+                    const uint8_t* src = (const uint8_t*)p.wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
+                    if ((p.dbg & 8) && issued >= C::STAGES) {
+                        mbar_expect_tx(full_b(stage), 0);
+                    } else {
+                        mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
+                        bulk_g2s(dst, src, 2 * C::B_TILE_BYTES, full_b(stage));
+                    }
+                    ++issued;
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-        // drain
-        while (inflight > 0) {
-            if (inflight >= 3) cp_async_wait<2>(); else if (inflight == 2) cp_async_wait<1>(); else cp_async_wait<0>();
-            signal_oldest();
-        }
-    } else if (warp == W_BLOAD) {
-        if (lane == 0) {
+    } else if (warp == W_FENCE) {
+        // ===================== proxy fence on behalf of the MMA lane =====================
+        // The producers write shared memory through the generic proxy (cp.async), tcgen05.mma reads it through the
+        // async proxy, so a fence.proxy.async has to sit between.  In the producers it lowers to MEMBAR.ALL.CTA and
+        // stalls on their own in-flight copies; in the MMA lane it costs 130-650 clk per chunk that are serial with
+        // MMA issue (timeline trace).  This lane has nothing else to do.
+        if (lane == 0 && helper_fence) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int ch = 0; ch < nchunks; ++ch) {
-                    mbar_wait(empty(stage), phase ^ 1u);
-                    const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
-                    const uint8_t* src = (const uint8_t*)p.wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
-                    mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
-                    bulk_g2s(dst, src, 2 * C::B_TILE_BYTES, full_b(stage));
+                    mbar_wait(full_a(stage), phase);
+                    fence_proxy_async();
+                    mbar_arrive(ready_a(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == W_MMA) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, 0u /*F16*/);
+            // x*w = ah*bh + (ah*bl + al*bh)/2048 as TWO instructions per K=16 step: ah x [bh | bl] (N = 2*BN, the
+            // weight block's hi and lo rows are contiguous) -> big and small1, al x bh (N = BN) -> small2.  An SS-mode
+            // MMA is paced by its operand reads (~64 B/clk: 4 KB of A + 32 B per B row), so sharing the A read between
+            // two of the three products takes 22 % off the tensor time (measured 96 clk per 128x64x16 instruction).
+            constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN, 0u /*F16*/), idesc1 = make_idesc(BM, BN, 0u);
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
+            int acc = 0, tchunk = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
+                const uint32_t d_big = tmem_base + (uint32_t)(acc * C::ACC_COLS), d_small2 = d_big + (uint32_t)(2 * BN);
                 for (int ch = 0; ch < nchunks; ++ch) {
-                    mbar_wait(full_a(stage), phase);
+                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && tchunk < TRACE_CHUNKS;
+                    long long ts0 = 0, ts1 = 0, ts2 = 0;
+                    if (tr) ts0 = clock64();
+                    if (helper_fence) {
+                        mbar_wait(ready_a(stage), phase);
+                    } else {
+                        mbar_wait(full_a(stage), phase);
+                        fence_proxy_async();
+                    }
+                    if (tr) ts1 = clock64();
                     mbar_wait(full_b(stage), phase);
                     tc_fence_after();
+                    if (tr) ts2 = clock64();
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;      // b_lo follows at + B_TILE_BYTES
                     // channels beyond cin are zero in both operands: issue only the K=16 steps that carry data
-                    const int ksteps = min(4, (p.cin - (ch % kchunks) * BKC + 15) / 16);
+                    const int ksteps = (p.dbg & 16) ? 0 : min(4, (p.cin - (ch % kchunks) * BKC + 15) / 16);
                     for (int k16 = 0; k16 < ksteps; ++k16) {
                         const uint32_t ko = (uint32_t)k16 * 32u;
-                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        mma_f16(d_small, dal, dbh, idesc, (ch | k16) ? 1u : 0u);
-                        mma_f16(d_small, dah, dbl, idesc, 1u);
-                        mma_f16(d_big, dah, dbh, idesc, (ch | k16) ? 1u : 0u);
+                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko), db = make_desc(b_hi + ko);
+                        const uint32_t accum = (ch | k16) ? 1u : 0u;
+                        mma_f16(d_big, dah, db, idesc2, accum);
+                        mma_f16(d_small2, dal, db, idesc1, accum);
                     }
                     mma_commit(empty(stage));
+                    if (tr) {
+                        long long* q = p.trace + (size_t)(2 * TRACE_CHUNKS + tchunk) * 4;
+                        q[0] = ts0; q[1] = ts1; q[2] = ts2; q[3] = clock64();
+                    }
+                    ++tchunk;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
                 mma_commit(tmem_full(acc));
@@ -200,29 +292,59 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         int acc = 0;
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
+        const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
             __syncwarp();
             tc_fence_after();
             const int m = tile * BM + r;
-            constexpr int CW = (BN >= 32) ? 32 : 16;
+            constexpr int CW = 16;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CW) {
-                uint32_t v[CW], u[CW];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 2 * BN + c0);
+                uint32_t v[CW], u[CW], w[CW];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + c0);
                 tmem_ld<CW>(v, taddr);
                 tmem_ld<CW>(u, taddr + (uint32_t)BN);
+                tmem_ld<CW>(w, taddr + (uint32_t)(2 * BN));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + CW >= BN) {      // accumulators are in registers: release the buffer to the MMA lane
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty(acc));
+                }
                 if (m < M) {
                     float o[CW];
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) {
+                    for (int j = 0; j < CW; j += 4) {
                         const int n = c0 + j;
-                        const float sc = (p.scale && n < p.cout) ? __ldg(&p.scale[n]) : 1.f;
-                        const float sh = (p.shift && n < p.cout) ? __ldg(&p.shift[n]) : 0.f;
-                        float val = fmaf(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]) * (1.f / kF16LoScale)), sc, sh);
-                        if (p.relu) val = fmaxf(val, 0.f);
-                        o[j] = n < p.cout ? val : 0.f;
+                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (vec_ss) {
+                            if (n < p.cout) {
+                                sc = __ldg((const float4*)(p.scale + n));
+                                sh = __ldg((const float4*)(p.shift + n));
+                            }
+                        } else {
+                            if (p.scale) {
+                                if (n + 0 < p.cout) sc.x = __ldg(&p.scale[n + 0]);
+                                if (n + 1 < p.cout) sc.y = __ldg(&p.scale[n + 1]);
+                                if (n + 2 < p.cout) sc.z = __ldg(&p.scale[n + 2]);
+                                if (n + 3 < p.cout) sc.w = __ldg(&p.scale[n + 3]);
+                            }
+                            if (p.shift) {
+                                if (n + 0 < p.cout) sh.x = __ldg(&p.shift[n + 0]);
+                                if (n + 1 < p.cout) sh.y = __ldg(&p.shift[n + 1]);
+                                if (n + 2 < p.cout) sh.z = __ldg(&p.shift[n + 2]);
+                                if (n + 3 < p.cout) sh.w = __ldg(&p.shift[n + 3]);
+                            }
+                        }
+                        const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float small = __fadd_rn(__uint_as_float(u[j + e]), __uint_as_float(w[j + e]));
+                            float val = fmaf(__fadd_rn(__uint_as_float(v[j + e]), small * (1.f / kF16LoScale)), scs[e], shs[e]);
+                            if (p.relu) val = fmaxf(val, 0.f);
+                            o[j + e] = (n + e) < p.cout ? val : 0.f;
+                        }
                     }
                     if (p.out_f32) {
                         float* orow = p.out_f32 + (size_t)m * p.out_f32_stride;
@@ -250,9 +372,6 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(acc));
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
     }
@@ -307,6 +426,32 @@ extern "C" int sassd_spconv_f16x3(const sassd_spconv_desc* d, const void* in_spl
     a.out_split = (__half*)out_split; a.out_plane = (size_t)d->rows_cap * d->out_ch; a.out_f32 = out_f32;
     a.cin = d->cin; a.cout = d->cout; a.taps = d->taps; a.rows_cap = d->rows_cap; a.relu = d->relu;
     a.out_ch = d->out_ch; a.out_f32_stride = d->out_f32_stride;
+    static const int dbg = [] { const char* e = getenv("SASSD_SPS_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg = dbg;
+    a.trace = nullptr;
+    if (dbg & 64) {      // timing experiment: dump CTA 0's per-chunk clock stamps of this launch to stderr
+        static long long* trace = nullptr;
+        const size_t n = (size_t)3 * sps::TRACE_CHUNKS * 4;
+        if (!trace) cudaMalloc(&trace, n * sizeof(long long));
+        cudaMemsetAsync(trace, 0, n * sizeof(long long), (cudaStream_t)stream_);
+        a.trace = trace;
+        const int rc = d->taps > 1 ? sps::dispatch3<1>(a, (cudaStream_t)stream_) : sps::dispatch3<0>(a, (cudaStream_t)stream_);
+        static int calls = 0;
+        if (rc == SASSD_OK && d->taps > 1 && d->rows_cap >= 1024 && ++calls == 3) {
+            std::vector<long long> h(n);
+            cudaStreamSynchronize((cudaStream_t)stream_);
+            cudaMemcpy(h.data(), trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+            long long t0 = 0;
+            for (size_t i = 0; i < n; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+            for (int ag = 0; ag < 3; ++ag)
+                for (int c = 0; c < sps::TRACE_CHUNKS; ++c) {
+                    const long long* q = &h[((size_t)ag * sps::TRACE_CHUNKS + c) * 4];
+                    fprintf(stderr, "TRACE %d %d %lld %lld %lld %lld\n", ag, c, q[0] ? q[0] - t0 : -1, q[1] ? q[1] - t0 : -1,
+                            q[2] ? q[2] - t0 : -1, q[3] ? q[3] - t0 : -1);
+                }
+        }
+        return rc;
+    }
     return d->taps > 1 ? sps::dispatch3<1>(a, (cudaStream_t)stream_) : sps::dispatch3<0>(a, (cudaStream_t)stream_);
 }
 

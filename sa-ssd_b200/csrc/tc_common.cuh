@@ -107,6 +107,43 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+// Same instruction with the A-operand collector: `keep` leaves A in the tensor core's collector buffer after this
+// MMA, `reuse` takes A from there instead of reading shared memory again (SASS: UTCHMMA ... A_KEEP / A_REUSE).
+__device__ __forceinline__ void mma_f16_akeep(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_areuse(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// Weight-stationary form: the B operand can stay in collector buffer b0 (SASS: UTCHMMA.WS ... B_KEEP / B_REUSE).
+// mode 0 = plain, 1 = fill b0, 2 = last use of b0.
+template <int MODE>
+__device__ __forceinline__ void mma_f16_ws(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    if constexpr (MODE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+    else if constexpr (MODE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
 template <int PREC>
 __device__ __forceinline__ void mma_any(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
     if constexpr (PREC == 0) mma_tf32(tmem_d, da, db, idesc, accum); else mma_f16(tmem_d, da, db, idesc, accum);
