@@ -179,12 +179,17 @@ int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int
 /* Ruled sparse conv on "split rows" (two fp16 planes [2][rows][C], C % 8 == 0; hi = half(x), lo = half((x-hi)*2048)):
  * same semantics as sassd_gconv TABLE / ROWS mode with SASSD_PREC_F16X3, but the gather is 16-byte cp.async copies
  * straight into the tensor-core operand tiles and the epilogue writes the next layer's planes (out_split, out_ch
- * channels, zero beyond cout) and/or fp32 rows.  taps == 1: row(m) = m.  cout <= 64. */
+ * channels, zero beyond cout) and/or fp32 rows.  taps == 1: row(m) = m.  cin <= 64, cout <= 64. */
 typedef struct {
     int32_t cin, cout, taps;         /* cin = stored channels of the input planes */
     int32_t rows_cap, in_rows_cap;   /* output rows capacity; rows of the input planes (plane stride) */
     int32_t relu, out_ch, out_f32_stride;
 } sassd_spconv_desc;
+/* wpack for sassd_spconv_f16x3: weight [taps, cin, cout] fp32 -> sassd_spconv_pack_bytes(taps, cin_stored, cout)
+ * bytes.  Narrow inputs are tap-packed: a 64-wide K chunk holds 64 / cin_stored taps (cin_stored 8, 16, 32). */
+size_t sassd_spconv_pack_bytes(int taps, int cin_stored, int cout);
+int sassd_spconv_pack(const float* weight, int taps, int cin, int cin_stored, int cout, void* packed,
+                      sassd_stream_t stream);
 int sassd_spconv_f16x3(const sassd_spconv_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
                        const float* shift, const int32_t* nbr, const int32_t* d_rows, void* out_split, float* out_f32,
                        sassd_stream_t stream);

@@ -85,8 +85,12 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.d_rows ? min(__ldg(p.d_rows), p.rows_cap) : p.rows_cap;
     const int ntiles = (M + BM - 1) / BM;
-    const int kchunks = (p.cin + BKC - 1) / BKC;
-    const int nchunks = p.taps * kchunks;
+    // Tap packing: a chunk is 64 K-columns = `tpg` taps of `cin` stored channels each (cin 8/16/32 -> 8/4/2 taps per
+    // chunk), so the narrow early layers run 4/7/14 chunks per tile instead of 27.  The weight pack has the same
+    // K order (sassd_spconv_pack).
+    const int ppt = p.cin >> 3;                              // 16-byte pieces per tap
+    const int tpg = (BKC % p.cin == 0) ? BKC / p.cin : 1;    // taps per chunk
+    const int nchunks = (p.taps + tpg - 1) / tpg;
     const bool nbr_tiles = TABLE && p.taps <= 27;
     const bool helper_fence = !(p.dbg & 128);
 
@@ -136,40 +140,39 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                 if (lane == 0) mbar_wait(nbr_full(nb), nb_phase);
                 __syncwarp();
             }
-            for (int t = 0; t < p.taps; ++t) {
-                int src = -1;
-                if (m < M) src = TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
-                const __half* rowp = p.in + (size_t)(src < 0 ? 0 : src) * p.cin;
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && pt == 0 && tchunk < TRACE_CHUNKS;
-                    long long ts0 = 0, ts1 = 0;
-                    if (tr) ts0 = clock64();
-                    // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
-                    // word slow every other barrier operation of the CTA)
-                    if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
-                    __syncwarp();
-                    if (tr) ts1 = clock64();
-                    const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
-                    if (!(p.dbg & 32)) {
+            for (int g = 0; g < nchunks; ++g) {
+                const bool tr = (p.dbg & 64) && blockIdx.x == 0 && pt == 0 && tchunk < TRACE_CHUNKS;
+                long long ts0 = 0, ts1 = 0;
+                if (tr) ts0 = clock64();
+                // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
+                // word slow every other barrier operation of the CTA)
+                if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
+                __syncwarp();
+                if (tr) ts1 = clock64();
+                const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
+                if (!(p.dbg & 32)) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int q = hf * 4 + c;                        // 16-byte piece (8 channels) of the row
-                            const int k = kc * BKC + q * 8;
-                            const uint32_t nbytes = (src >= 0 && k < p.cin) ? 16u : 0u;   // 0 -> hardware zero fill
-                            const __half* sp = rowp + (nbytes ? k : 0);
-                            const uint32_t off = ((uint32_t)q ^ sw) << 4;
-                            cp_async16(a_hi + off, sp, nbytes);
-                            cp_async16(a_lo + off, sp + p.in_plane, nbytes);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        const int q = hf * 4 + c;                        // 16-byte piece (8 K-columns) of the row
+                        const int tl = q / ppt, piece = q - tl * ppt;    // tap within the chunk, piece within the tap
+                        const int t = g * tpg + tl;
+                        int src = -1;
+                        if (m < M && tl < tpg && t < p.taps)
+                            src = TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
+                        const uint32_t nbytes = src >= 0 ? 16u : 0u;     // 0 -> hardware zero fill
+                        const __half* sp = p.in + (size_t)(src < 0 ? 0 : src) * p.cin + (nbytes ? piece * 8 : 0);
+                        const uint32_t off = ((uint32_t)q ^ sw) << 4;
+                        cp_async16(a_hi + off, sp, nbytes);
+                        cp_async16(a_lo + off, sp + p.in_plane, nbytes);
                     }
-                    cp_async_arrive_noinc(full_a(stage));
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-                    if (tr) {
-                        long long* q = p.trace + (size_t)(0 * TRACE_CHUNKS + tchunk) * 4;
-                        q[0] = ts0; q[1] = ts1; q[2] = clock64(); q[3] = 0;
-                    }
-                    ++tchunk;
                 }
+                cp_async_arrive_noinc(full_a(stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                if (tr) {
+                    long long* q = p.trace + (size_t)(0 * TRACE_CHUNKS + tchunk) * 4;
+                    q[0] = ts0; q[1] = ts1; q[2] = clock64(); q[3] = 0;
+                }
+                ++tchunk;
             }
             if (nbr_tiles) {
                 __syncwarp();
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                     const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;      // b_lo follows at + B_TILE_BYTES
                     // channels beyond cin are zero in both operands: issue only the K=16 steps that carry data
-                    const int ksteps = (p.dbg & 16) ? 0 : min(4, (p.cin - (ch % kchunks) * BKC + 15) / 16);
+                    const int ksteps = (p.dbg & 16) ? 0 : min(4, (min(tpg, p.taps - ch * tpg) * p.cin + 15) / 16);
                     for (int k16 = 0; k16 < ksteps; ++k16) {
                         const uint32_t ko = (uint32_t)k16 * 32u;
                         const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko), db = make_desc(b_hi + ko);
@@ -411,11 +414,53 @@ static int dispatch3(const Args& a, cudaStream_t s) {
 
 }  // namespace sps
 
+// Weight packer for sassd_spconv_f16x3: W [taps, cin, cout] fp32 -> per chunk [hi | lo][BN rows][64 K-columns] fp16,
+// 128B-swizzled, K-column = (tap within chunk) * cin_stored + channel.
+__global__ void spconv_pack_kernel(const float* __restrict__ w, int taps, int cin, int cs, int cout, int bn, int tpg,
+                                   int nchunks, __half* __restrict__ out) {
+    const long long per_chunk = 2LL * bn * 64;
+    const long long total = (long long)nchunks * per_chunk;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / per_chunk);
+        long long rem = i % per_chunk;
+        const int part = (int)(rem / (bn * 64));          // 0 = hi, 1 = lo
+        rem %= (bn * 64);
+        const int n = (int)(rem / 64), pos = (int)(rem % 64);
+        const int kk = (((pos >> 3) ^ (n & 7)) << 3) + (pos & 7);   // logical K-column stored at this physical slot
+        const int tl = kk / cs, ch = kk % cs, t = g * tpg + tl;
+        float v = 0.f;
+        if (tl < tpg && t < taps && ch < cin && n < cout) v = w[((size_t)t * cin + ch) * cout + n];
+        float hi, lo;
+        tc::split_f16(v, hi, lo);
+        out[i] = __float2half_rn(part == 0 ? hi : lo);
+    }
+}
+
+static int spconv_bn(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
+static int spconv_tpg(int cs) { return (64 % cs == 0) ? 64 / cs : 1; }
+
+extern "C" size_t sassd_spconv_pack_bytes(int taps, int cin_stored, int cout) {
+    if (taps < 1 || cin_stored < 8 || (cin_stored & 7) || cin_stored > 64 || cout < 1 || cout > 64) return 0;
+    const int tpg = spconv_tpg(cin_stored);
+    return (size_t)((taps + tpg - 1) / tpg) * 2 * spconv_bn(cout) * 128;
+}
+
+extern "C" int sassd_spconv_pack(const float* weight, int taps, int cin, int cin_stored, int cout, void* packed,
+                                 sassd_stream_t stream_) {
+    if (!weight || !packed || cin < 1 || cin > cin_stored || !sassd_spconv_pack_bytes(taps, cin_stored, cout))
+        return SASSD_ERR_ARG;
+    const int tpg = spconv_tpg(cin_stored), nchunks = (taps + tpg - 1) / tpg, bn = spconv_bn(cout);
+    spconv_pack_kernel<<<sassd_grid((long long)nchunks * 2 * bn * 64, 256), 256, 0, (cudaStream_t)stream_>>>(
+        weight, taps, cin, cin_stored, cout, bn, tpg, nchunks, (__half*)packed);
+    return sassd_check_launch();
+}
+
 extern "C" int sassd_spconv_f16x3(const sassd_spconv_desc* d, const void* in_split, const void* wpack,
                                   const float* scale, const float* shift, const int32_t* nbr, const int32_t* d_rows,
                                   void* out_split, float* out_f32, sassd_stream_t stream_) {
     if (!d || !in_split || !wpack || (!out_split && !out_f32)) return SASSD_ERR_ARG;
-    if (d->cin < 8 || (d->cin & 7) || d->cout < 1 || d->cout > 64 || d->taps < 1 || d->rows_cap < 0) return SASSD_ERR_ARG;
+    if (d->cin < 8 || (d->cin & 7) || d->cin > 64 || d->cout < 1 || d->cout > 64 || d->taps < 1 || d->rows_cap < 0)
+        return SASSD_ERR_ARG;
     if (d->taps > 1 && !nbr) return SASSD_ERR_ARG;
     if (out_split && ((d->out_ch & 7) || d->out_ch < d->cout)) return SASSD_ERR_ARG;
     if (out_f32 && (d->out_f32_stride & 3)) return SASSD_ERR_ARG;

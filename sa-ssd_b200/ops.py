@@ -47,7 +47,7 @@ def next_pow2(n):
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
             "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
-            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_conv2d_f16x3": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_spconv_pack": 1, "sassd_conv2d_f16x3": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
 LAUNCHES = 0          # running count of kernels launched through this module
@@ -211,6 +211,26 @@ def tc_pack_cached(weight, precision):
         if len(_TC_PACKS) >= 256:
             _TC_PACKS.pop(next(iter(_TC_PACKS)))
         ent = (pack_tc(weight.contiguous(), precision), weight)
+        _TC_PACKS[key] = ent
+    return ent[0]
+
+
+def spconv_pack_cached(weight, cin_stored):
+    """Tap-packed fp16 hi/lo weight blocks for sassd_spconv_f16x3 (cached like tc_pack_cached)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), "spconv", cin_stored)
+    ent = _TC_PACKS.get(key)
+    if ent is None:
+        if len(_TC_PACKS) >= 256:
+            _TC_PACKS.pop(next(iter(_TC_PACKS)))
+        w = weight.contiguous()
+        taps, cin, cout = w.shape
+        nbytes = _L().sassd_spconv_pack_bytes(taps, cin_stored, cout)
+        if nbytes == 0:
+            raise _lib.SassdError("sassd_spconv_pack_bytes: unsupported shape taps=%d cin_stored=%d cout=%d"
+                             % (taps, cin_stored, cout))
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+        _call("sassd_spconv_pack", None, _ptr(w), taps, cin, cin_stored, cout, _ptr(packed), _stream())
+        ent = (packed, weight)
         _TC_PACKS[key] = ent
     return ent[0]
 
@@ -396,7 +416,7 @@ def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d
     """planes [2, in_cap, cin_stored] fp16; weight [taps, cin, cout] fp32 (packed on first use).
     Returns (out planes [2, rows_cap, out_ch], fp32 rows or None)."""
     taps = weight.shape[0]
-    wp = tc_pack_cached(weight, PREC_F16X3)
+    wp = spconv_pack_cached(weight, planes.shape[2])
     d = SpconvDesc()
     d.cin, d.cout, d.taps = planes.shape[2], cout, taps
     d.rows_cap, d.in_rows_cap, d.relu = rows_cap, planes.shape[1], 1 if relu else 0

@@ -578,3 +578,21 @@ def test_density_sweep_endpoints(dev, car_model):
             _compare_frame(out[b], (exp[0][b], exp[1][b], exp[2][b]), "sweep frame %d" % b)
         else:   # heavy-tailed synthetic activations: threshold decisions may flip within 1e-4 of the scale
             assert abs(gg - ge) <= max(2, ge // 20), (gg, ge)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stage,env", [("tma", {}), ("tma", {"SASSD_TMA_PAIR": "1"}), ("split", {})])
+def test_tcgen05_kernel_unit_checks(stage, env):
+    """tests/tools/tc_check.py compares the TMA dense conv (single-CTA and the opt-in CTA-pair kernel) and the
+    split-row sparse conv with fp64 references over the shape/edge cases of the pipeline; a fresh process because
+    the kernel selection is read from the environment once."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "tc_check.py"), stage], cwd=root, env=e,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count(" OK") >= 7, r.stdout[-3000:]
