@@ -160,12 +160,19 @@ def algorithmic_work(aux, batch):
     return tot_b, tot_f, pairs
 
 
+# DRAM bytes of one B=1 launch of the roofline kernel, from the committed `ncu --set full` capture
+NCU_DRAM_BYTES_PER_LAUNCH = {"tma::conv2d_tma_kernel<256>": 38518016 + 2328064}
+
+
 def profile_step(model, points, pt_off, batch, maxpts, iters=3):
     """Per-C-ABI-call CUDA-event timing of one step (events on the launching stream)."""
     from sassd_b200 import ops
     agg = {}
     for _ in range(iters):
         ops.PROFILE = []
+        # hold the GPU for ~3 ms so that the host has queued the whole step before the first kernel starts: the
+        # event pairs then bracket back-to-back kernels instead of kernel + host launch latency
+        torch.cuda._sleep(6_000_000)
         det, nd, status, aux = model.forward_device(points, pt_off, batch, maxpts)
         torch.cuda.synchronize()
         for name, label, e0, e1 in ops.PROFILE:
@@ -258,16 +265,35 @@ def run_ours(args, rank, world, local):
     # ---- e2e through the public API: host numpy points -> pinned -> H2D -> path -> D2H detections
     # throughput API: detect_stream (double-buffered CUDA graphs; H2D of step i+1 overlaps the GPU work of step i)
     maxpts_e2e = ops.next_pow2(max(max(p.shape[0] for p in fb) for fb in batches))
-    for _ in model.detect_stream([batches[i % pool] for i in range(3)], B, maxpts_e2e):
+    for _ in model.detect_stream([batches[i % pool] for i in range(2 * args.in_flight)], B, maxpts_e2e,
+                                 depth=args.in_flight, concurrent=not args.serial_stream):
         pass
     D.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     ndet = 0
-    for out in model.detect_stream((batches[i % pool] for i in range(args.steps)), B, maxpts_e2e):
+    for out in model.detect_stream((batches[i % pool] for i in range(args.steps)), B, maxpts_e2e,
+                                   depth=args.in_flight, concurrent=not args.serial_stream):
         ndet += sum(0 if o["boxes_lidar"] is None else len(o["boxes_lidar"]) for o in out)
     torch.cuda.synchronize()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
     e2e = world * args.steps * B / e2e_s
+    # the same stream with one step on the GPU at a time, for comparison
+    t0 = time.perf_counter()
+    for out in model.detect_stream((batches[i % pool] for i in range(args.steps)), B, maxpts_e2e,
+                                   depth=args.in_flight, concurrent=False):
+        pass
+    torch.cuda.synchronize()
+    e2e_serial = world * args.steps * B / D.max_over_ranks(time.perf_counter() - t0, dev)
+    if os.environ.get("SASSD_BENCH_DEPTHS") and rank == 0:      # experiment: other numbers of steps in flight
+        for dpt in [int(v) for v in os.environ["SASSD_BENCH_DEPTHS"].split(",")]:
+            for _ in model.detect_stream([batches[i % pool] for i in range(2 * dpt)], B, maxpts_e2e, depth=dpt):
+                pass
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for out in model.detect_stream((batches[i % pool] for i in range(args.steps)), B, maxpts_e2e, depth=dpt):
+                pass
+            torch.cuda.synchronize()
+            print("in-flight %d: %.1f frames/s" % (dpt, args.steps * B / (time.perf_counter() - t0)), file=sys.stderr)
     # latency of the synchronous single call (stage + H2D + graph + D2H + sync), for reference
     t0 = time.perf_counter()
     for i in range(min(args.steps, 10)):
@@ -299,7 +325,10 @@ def run_ours(args, rank, world, local):
                   "mixed": "3 TF32 MMA passes per algorithmic flop",
                   "f16x3": "3 FP16 MMA passes per algorithmic flop (ceiling 1/3 of the fp16/bf16 peak)"}[args.precision]
         roofline = dict(kernel="%s (BEVNet 3x3 256->256, %d launches/step)" % (kname, bev["calls_per_step"]),
-                        bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                        bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                        traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(kname) and NCU_DRAM_BYTES_PER_LAUNCH[kname] * B,
+                        traffic_unit="bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of the B=1 launch "
+                                     "in profiles/r1_ncu_full_conv2d_tma.md, scaled by the batch",
                         peak_source="%s bf16 dense, sustained" % peaks["source"],
                         note="achieved = algorithmic fp32 flops / CUDA-event time; " + passes,
                         mma_issue_frac=(3.0 if args.precision != "fp32" else 1.0) * ach / peak *
@@ -310,7 +339,7 @@ def run_ours(args, rank, world, local):
     sp_kernel = {"fp32": "gconv_ffma_kernel<TABLE,...>", "mixed": "gconv_ffma_kernel<TABLE,...>"}.get(
         args.precision, "tc::gconv_tc_kernel<TABLE,BN,1,%s>" % args.precision.upper())
     if any(k.startswith("spconv_split") for k in prof):
-        sp_kernel = "sps::spconv_split_kernel<TABLE,BN> (cp.async gather of split fp16 rows, tcgen05 FP16x3)"
+        sp_kernel = "sps::spconv_split_kernel<TABLE,BN> (async cp.async gather of split fp16 rows, tap-packed tcgen05 FP16x3)"
     sp_ach = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
     roofline_sparse = dict(kernel=sp_kernel + " x13 ruled sparse convs", bound="hbm", achieved=sp_ach,
                            peak=peaks["hbm_gbs"], unit="GB/s", frac=sp_ach / peaks["hbm_gbs"], traffic=None,
@@ -347,6 +376,7 @@ def run_ours(args, rank, world, local):
                 clocks=clocks, gpu_launches=launches,
                 e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          api="SingleStageDetector.detect_stream (host numpy points in, numpy detections out)",
+                         steps_in_flight=1 if args.serial_stream else args.in_flight, value_one_step_in_flight=e2e_serial,
                          sync_call_ms=sync_ms),
                 roofline=roofline, roofline_sparse=roofline_sparse, cpu_baseline=cpu,
                 stages_ms=stages, dominant=dom[0], wall_s=t_wall, detections_e2e=ndet)
@@ -363,6 +393,9 @@ def main():
     ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "f16x3", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--serial-stream", action="store_true",
+                    help="e2e: one step on the GPU at a time (default: detect_stream keeps --in-flight captured steps going)")
+    ap.add_argument("--in-flight", type=int, default=4, help="captured steps detect_stream keeps in flight (e2e)")
     args = ap.parse_args()
     from sassd_b200 import dist as D
     if args.impl == "reference":

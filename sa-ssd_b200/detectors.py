@@ -160,10 +160,12 @@ class SingleStageDetector(nn.Module):
     def disable_cuda_graph(self):
         self._graph = None
 
-    def detect_stream(self, batches, batch, max_points_per_frame=32768, depth=2):
+    def detect_stream(self, batches, batch, max_points_per_frame=32768, depth=4, concurrent=True):
         """Throughput API: iterate over batches (each a list of ``batch`` raw point arrays) and yield their
-        detections in order.  ``depth`` captured graphs with their own static buffers are used round-robin:
-        while the GPU runs step i, the host stages and uploads step i+1 (copy stream) and unpacks step i-1."""
+        detections in order.  ``depth`` captured graphs with their own static buffers and scratch are used
+        round-robin: while the GPU runs step i, the host stages and uploads step i+1 (copy stream) and unpacks
+        step i-1.  With ``concurrent`` every slot replays on its own stream, so the low-occupancy phases of one
+        step (voxelize, rulebooks, the sparse layers, NMS) run beside the dense layers of its neighbour."""
         ops.require_cuda()
         key = (batch, max_points_per_frame, depth)
         if getattr(self, "_stream_key", None) != key:
@@ -180,7 +182,7 @@ class SingleStageDetector(nn.Module):
             if not slot.fits(len(fb), counts):
                 raise ValueError("batch does not fit the captured shape (batch %d, %d points/frame)" %
                                  (batch, max_points_per_frame))
-            slot.submit(fb, counts, self._copy_stream)
+            slot.submit(fb, counts, self._copy_stream, own_stream=concurrent)
             pending.append(slot)
         for slot in pending:
             bbs, scs, lbs = slot.collect()
@@ -234,17 +236,25 @@ class _GraphedStep:
         self.cap = self.batch * self.maxpts
         self.points = torch.zeros((self.cap, 4), dtype=torch.float32, device=dev)
         self.pt_off = torch.zeros((self.batch + 1,), dtype=torch.int32, device=dev)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):       # warm-up: workspaces, weight packs and folded BN get created eagerly
-            for _ in range(2):
-                model.forward_device(self.points, self.pt_off, self.batch, self.maxpts)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.det, self.d_ndet, self.status, self.aux = model.forward_device(self.points, self.pt_off, self.batch,
-                                                                                self.maxpts)
+        # Scratch buffers private to this graph (the captured kernels bake their addresses in), so that several
+        # captured steps can be in flight on different streams without sharing anything but read-only weights.
+        self.ws = ops.Workspace()
+        self.stream = torch.cuda.Stream(device=dev)
+        shared_ws, ops._WS = ops._WS, self.ws
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):   # warm-up: workspaces, weight packs and folded BN get created eagerly
+                for _ in range(2):
+                    model.forward_device(self.points, self.pt_off, self.batch, self.maxpts)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.det, self.d_ndet, self.status, self.aux = model.forward_device(self.points, self.pt_off,
+                                                                                    self.batch, self.maxpts)
+        finally:
+            ops._WS = shared_ws
         self.h_det = torch.empty(self.det.shape, dtype=torch.float32, pin_memory=True)
         self.h_nd = torch.empty(self.d_ndet.shape, dtype=torch.int32, pin_memory=True)
         self.h_status = torch.empty((1,), dtype=torch.int32, pin_memory=True)
@@ -276,21 +286,23 @@ class _GraphedStep:
         return self.unpack()
 
     # ---- asynchronous use (SingleStageDetector.detect_stream): submit() ... collect()
-    def submit(self, points_list, counts, copy_stream):
-        """Stage into this slot's pinned buffer, H2D on the copy stream, replay + D2H on the current stream."""
+    def submit(self, points_list, counts, copy_stream, own_stream=False):
+        """Stage into this slot's pinned buffer, H2D on the copy stream, then replay + D2H on the current stream or,
+        with ``own_stream``, on this slot's stream so that consecutive steps overlap on the GPU."""
         _stage_into(self.h_points, self.h_off, points_list, counts)
         total = sum(counts)
-        cur = torch.cuda.current_stream()
+        cur = self.stream if own_stream else torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
             self.points[:total].copy_(self.h_points[:total], non_blocking=True)
             self.pt_off.copy_(self.h_off, non_blocking=True)
             self.loaded.record(copy_stream)
         cur.wait_event(self.loaded)
-        self.graph.replay()
-        self.h_det.copy_(self.det, non_blocking=True)
-        self.h_nd.copy_(self.d_ndet, non_blocking=True)
-        self.h_status.copy_(self.status, non_blocking=True)
-        self.done.record(cur)
+        with torch.cuda.stream(cur):
+            self.graph.replay()
+            self.h_det.copy_(self.det, non_blocking=True)
+            self.h_nd.copy_(self.d_ndet, non_blocking=True)
+            self.h_status.copy_(self.status, non_blocking=True)
+            self.done.record(cur)
 
     def collect(self):
         self.done.synchronize()
