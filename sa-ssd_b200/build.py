@@ -52,7 +52,19 @@ def build(force=False, verbose=False):
         objs = list(ex.map(cc, sources()))
     cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.check_call(cmd)
+    build_probe(force)
     return LIB
+
+
+def build_probe(force=False):
+    """tests/tools/ts_probe: the tcgen05 instruction-rate microbenchmark (measurement tool, not part of the library)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "tools", "ts_probe.cu")
+    exe = src[:-3]
+    if os.path.exists(src) and (force or not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src)):
+        subprocess.check_call(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", CSRC,
+                               src, "-o", exe])
+    return exe
 
 
 if __name__ == "__main__":

@@ -3,12 +3,14 @@
 // two fp16 planes [2][rows_cap][C] (hi = half(x), lo = half((x - hi) * 2048)), C a multiple of 8.
 //
 // Why: ncu on gconv_tc.cu's TABLE mode (fp32 rows gathered through registers, split on the fly) shows the
-// producers — not the tensor pipe (28 %), not L2 (14 %) — as the limit: ~250 instructions per warp and chunk at
-// IPC 0.36 with long-scoreboard stalls.  Here a producer thread only *issues* eight 16-byte cp.async copies per
-// chunk (zero-fill for missing neighbours and for channels beyond C) straight into the 128B-swizzled operand
-// tiles; no registers are staged and no split math runs in the main loop (the producing layer's epilogue wrote
-// the planes).  cp.async groups give a 3-chunk-deep gather pipeline; completion -> fence.proxy.async -> one
-// mbarrier arrive per warp hands the tile to the MMA lane.
+// producers — not the tensor pipe (28 %), not L2 (14 %) — as the limit.  Here a producer thread only *issues* eight
+// 16-byte cp.async copies per chunk (zero fill for missing neighbours) straight into the 128B-swizzled operand tiles
+// and one asynchronous mbarrier arrive that fires when they have landed; no thread waits for data, no registers
+// are staged and no split math runs in the main loop (the producing layer's epilogue wrote the planes).  The per-chunk
+// timeline of a CTA (SASSD_SPS_DBG=64, profiles/r1_timeline_spconv_split.md) then shows the MMA-issuing lane as the
+// critical path, so everything else is taken off it: a helper warp does the generic->async proxy fence, the tile's
+// neighbour indices arrive by one bulk copy, two MMAs per K=16 step instead of three (N-concatenated weights), and
+// the narrow layers pack several taps into one 64-wide K chunk.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
