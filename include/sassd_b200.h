@@ -253,6 +253,23 @@ int sassd_nms_sorted(const float* boxes5, int n, float thr, int64_t* keep, int32
 /* iou3d_cuda.boxes_iou_bev_gpu (iou3d.cpp:52-71): dense [na, nb] rotated BEV IoU. */
 int sassd_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* iou, sassd_stream_t stream);
 
+/* ---- KITTI evaluation support ----------------------------------------------------
+ * Rotated-box overlap of the reference's evaluator (mmdet/core/post_processing/rotate_nms_gpu.py:536-627
+ * rotate_iou_gpu_eval), batched over frames: boxes / query are concatenated [sum, 5] (x, y, dx, dy, angle) arrays
+ * with per-frame offsets [nframes + 1]; out[out_off[f] + n * nq_f + k] = overlap(box n, query k) of frame f.
+ * criterion: -1 IoU, 0 intersection / area(query), 1 intersection / area(box), 2 intersection area. */
+int sassd_rotate_overlap_eval(const float* boxes, const int32_t* box_off, const float* query, const int32_t* query_off,
+                              const int64_t* out_off, int nframes, int criterion, int max_pairs_per_frame, float* out,
+                              sassd_stream_t stream);
+/* HOST function (all pointers are host memory): greedy GT<->detection matching of the KITTI protocol
+ * (mmdet/core/evaluation/kitti_eval.py:164-283, :295-342).  nthresh == 0: collect the scores of the true positives
+ * (tp_scores capacity = number of gt rows); nthresh > 0: pr[t] += (tp, fp, fn, similarity) for every threshold. */
+int sassd_kitti_match(int nframes, const double* overlaps, const int64_t* ov_off, const int32_t* gt_off,
+                      const int32_t* dt_off, const int32_t* dc_off, const double* gt_alpha, const double* dt_alpha,
+                      const double* dt_score, const double* dt_bbox, const double* dc_bbox, const int32_t* ign_gt,
+                      const int32_t* ign_dt, int metric, double min_overlap, int compute_aos, int nthresh,
+                      const double* thresholds, double* pr, double* tp_scores, int64_t* n_tp_scores);
+
 #ifdef __cplusplus
 }
 #endif

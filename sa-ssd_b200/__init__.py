@@ -9,6 +9,7 @@ __version__ = "0.1.0"
 
 from .config import Config, obj_from_dict  # noqa: F401
 from .results import Calibration, kitti_bbox2results  # noqa: F401
+from .kitti_eval import get_official_eval_result  # noqa: F401
 
 
 def build_from_config(cfg, device="cuda", data_key="val"):

@@ -8,6 +8,7 @@ evaluation code:
 * `Calibration`         <- mmdet/datasets/kitti_utils.py:49-107 (the fields the
   formatter reads: P2, V2C, R0), `read_calib_file` :109-125
 * `empty_result_anno`   <- tools/kitti_common.py:632-646
+* `kitti_result_line`, `annos_to_kitti_label` <- tools/kitti_common.py:413-471 (label / result file lines)
 
 This is float64 numpy on a few dozen boxes per frame; it stays on the host in
 the reference and here (not on the device path).
@@ -160,17 +161,39 @@ def kitti_bbox2results(boxes_lidar, scores, labels, meta, class_names=None):
     return {k: np.stack(v) for k, v in rows.items()}
 
 
-def format_kitti_lines(anno):
-    """One KITTI result-file line per detection (what the reference's
-    tools/kitti_common.py `kitti_result_line`/`annos_to_kitti_label` write)."""
-    lines = []
-    for i in range(len(anno['name'])):
-        b, d, l = anno['bbox'][i], anno['dimensions'][i], anno['location'][i]
-        # KITTI label order: h w l (dimensions are stored l h w)
-        lines.append(
-            '%s %.2f %d %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f '
-            '%.2f %.2f %.4f' % (
-                anno['name'][i], anno['truncated'][i], anno['occluded'][i],
-                anno['alpha'][i], b[0], b[1], b[2], b[3], d[1], d[2], d[0],
-                l[0], l[1], l[2], anno['rotation_y'][i], anno['score'][i]))
-    return lines
+_LINE_DEFAULTS = (('name', None), ('truncated', -1), ('occluded', -1), ('alpha', -10), ('bbox', None),
+                  ('dimensions', [-1, -1, -1]), ('location', [-1000, -1000, -1000]), ('rotation_y', -10),
+                  ('score', 0.0))
+
+
+def kitti_result_line(result_dict, precision=4):
+    """One line of a KITTI label/result file from a dict of fields (tools/kitti_common.py:413-453): fields in the
+    official order, floats with ``precision`` decimals, missing optional fields as their defaults."""
+    fmt = "{:.%df}" % precision
+    defaults = dict(_LINE_DEFAULTS)
+    for key in result_dict:
+        if key not in defaults:
+            raise ValueError("unknown key. supported key:{}".format([k for k, _ in _LINE_DEFAULTS]))
+    parts = []
+    for key, default in _LINE_DEFAULTS:
+        val = result_dict.get(key)
+        if val is None and default is None and key in result_dict:
+            raise ValueError("you must specify a value for {}".format(key))
+        if key == 'name':
+            parts.append(val)
+        elif key in ('truncated', 'alpha', 'rotation_y', 'score'):
+            parts.append(str(default) if val is None else fmt.format(val))
+        elif key == 'occluded':
+            parts.append(str(default) if val is None else '{}'.format(val))
+        else:
+            parts += [str(v) for v in default] if val is None else [fmt.format(v) for v in val]
+    return ' '.join(parts)
+
+
+def annos_to_kitti_label(annos, with_score=False):
+    """Lines of one frame's annotation dict (tools/kitti_common.py:455-471; the reference leaves the score out,
+    ``with_score`` appends it for result files)."""
+    keys = ['name', 'truncated', 'occluded', 'alpha', 'bbox', 'dimensions', 'location', 'rotation_y']
+    if with_score:
+        keys.append('score')
+    return [kitti_result_line({k: annos[k][i] for k in keys}) for i in range(len(annos['name']))]

@@ -62,6 +62,12 @@ def main():
         res = kitti_bbox2results(boxes.copy(), scores, labels, meta, names)
         for k, v in res.items():
             out['c%d_out_%s' % (ci, k)] = np.asarray(v)
+        if len(res['name']):
+            import tools.kitti_common as kitti
+            out['c%d_lines' % ci] = np.array(kitti.annos_to_kitti_label(res))
+            out['c%d_line0_scored' % ci] = np.array(kitti.kitti_result_line(
+                {k: res[k][0] for k in ('name', 'truncated', 'occluded', 'alpha', 'bbox', 'dimensions', 'location',
+                                        'rotation_y', 'score')}, precision=2))
         print(ci, {k: np.asarray(v).shape for k, v in res.items()})
     out['ncases'] = np.array(ci + 1)
     np.savez_compressed(os.path.join(HERE, 'results.npz'), **out)
