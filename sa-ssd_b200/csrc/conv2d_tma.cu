@@ -192,6 +192,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     volatile uint32_t* tmem_slot_ptr =
         (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + C::OUT_STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
+    pdl_launch_dependents();      // the next layer may be scheduled as this grid's CTAs retire
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.H + TILE_H - 1) / TILE_H;
     const int ntiles = p.batch * tiles_y * tiles_x;
@@ -214,6 +215,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                   // the producing layer has completed; nothing above touched global data
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == WARP_LOAD) {
@@ -556,7 +558,7 @@ static int launch2(const CUtensorMap& map, const CUtensorMap& omap, const Conv2d
     }
     const int tiles = a.batch * sassd_div_up(a.H, TILE_H) * sassd_div_up(a.W, TILE_W);
     const int grid = tiles < 148 ? tiles : 148;
-    kern<<<grid, THREADS2, C::SMEM_BYTES, stream>>>(map, omap, a);
+    if (launch_pdl(kern, dim3(grid), dim3(THREADS2), C::SMEM_BYTES, stream, map, omap, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
 }
 

@@ -84,9 +84,8 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 8);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + (tmem_slot - base));
 
+    pdl_launch_dependents();      // the next layer may be scheduled as this grid's CTAs retire
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int M = p.d_rows ? min(__ldg(p.d_rows), p.rows_cap) : p.rows_cap;
-    const int ntiles = (M + BM - 1) / BM;
     // Tap packing: a chunk is 64 K-columns = `tpg` taps of `cin` stored channels each (cin 8/16/32 -> 8/4/2 taps per
     // chunk), so the narrow early layers run 4/7/14 chunks per tile instead of 27.  The weight pack has the same
     // K order (sassd_spconv_pack).
@@ -117,6 +116,9 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                   // producing layer / rulebook complete; nothing above touched global data
+    const int M = p.d_rows ? min(__ldg(p.d_rows), p.rows_cap) : p.rows_cap;
+    const int ntiles = (M + BM - 1) / BM;
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ===================== A producers: cp.async gather of split rows =====================
@@ -402,7 +404,7 @@ static int launch3(const Args& a, cudaStream_t stream) {
     }
     int grid = sassd_div_up(a.rows_cap, BM);
     if (grid > 148) grid = 148;
-    kern<<<grid, THREADS3, C::SMEM_BYTES, stream>>>(a);
+    if (launch_pdl(kern, dim3(grid), dim3(THREADS3), C::SMEM_BYTES, stream, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
 }
 

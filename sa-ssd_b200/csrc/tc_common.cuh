@@ -5,6 +5,9 @@
 
 #include "common.cuh"
 
+#include <cstdlib>
+#include <utility>
+
 namespace tc {
 
 constexpr int BM = 128;
@@ -36,6 +39,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running.  launch_dependents lets the NEXT grid be scheduled as soon
+// as this grid's CTAs free their resources; wait blocks until every prerequisite grid has completed and its memory
+// is visible - nothing that reads or writes global data may run before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -216,6 +226,30 @@ __device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi2, uin
     const __half2 l = __floats2half2_rn((x - hf.x) * kF16LoScale, (y - hf.y) * kF16LoScale);
     hi2 = *reinterpret_cast<const uint32_t*>(&h);
     lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Host: launch `kern`, optionally (SASSD_PDL=1) as a programmatic dependent of the previous kernel in the stream.
+// Every kernel launched through here calls pdl_wait() before touching global data.  Off by default: measured
+// +0.9 % with one step on the GPU at a time, but -4.5 % with four captured steps in flight, where the early-resident
+// CTAs of the next layer sit on SMs that another frame's kernels could have used.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SASSD_PDL"); return e && atoi(e) != 0; }();
+    return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 }  // namespace tc
