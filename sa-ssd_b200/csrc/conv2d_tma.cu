@@ -11,8 +11,11 @@
 //     cp.async.bulk.tensor.4d box {64 ch, 16 x, 8 y, 1} at (y0+dy, x0+dx) — TMA writes it 128B-swizzled
 //     straight into the UMMA layout and zero-fills out-of-image pixels (= the conv's zero padding);
 //   * no producer warps: warp 4 lane 0 issues the TMA boxes (A hi, A lo) and the weight bulk copies,
-//     warp 5 lane 0 issues the MMAs, warps 0-3 drain TMEM.
-// The LSU / shared-memory store path is out of the main loop entirely.
+//     warp 5 lane 0 issues the MMAs (one operand of each K=16 step is read once for two of the three
+//     products: weight-stationary B collector at N=256, A collector otherwise), warps 0-3 drain TMEM,
+//     stage the next layer's split planes in 64B-swizzled shared memory and write them with TMA stores.
+// The LSU / shared-memory store path is out of the main loop entirely.  Where the time goes and what was
+// tried (stale loads, CTA pairs, N=128 instructions, collectors): profiles/r1_ncu_full_conv2d_tma.md.
 #include <cuda.h>
 
 #include <cstdlib>
