@@ -9,7 +9,14 @@ __version__ = "0.1.0"
 
 from .config import Config, obj_from_dict  # noqa: F401
 from .results import Calibration, kitti_bbox2results  # noqa: F401
-from .kitti_eval import get_official_eval_result  # noqa: F401
+
+
+def get_official_eval_result(gt_annos, dt_annos, current_classes, difficultys=(0, 1, 2)):
+    """KITTI official evaluation table (kitti_eval.get_official_eval_result; imported on first use because it
+    loads the native library)."""
+    from .kitti_eval import get_official_eval_result as impl
+    return impl(gt_annos, dt_annos, current_classes, list(difficultys))
+
 
 
 def build_from_config(cfg, device="cuda", data_key="val"):
