@@ -24,6 +24,17 @@ static inline int sassd_grid(long long work, int block, int ctas_per_sm = 8) {
     return (int)(need < cap ? need : cap);
 }
 
+// An active BEV cell (b, y, x) marks every SASSD_CONV2D_TILE_H x SASSD_CONV2D_TILE_W tile that contains it or has it
+// in its one-pixel halo (sassd_conv2d_f16x3_occ skips the tiles left at 0).  Plain stores of 1: races are benign.
+__device__ __forceinline__ void sassd_mark_conv2d_tiles(int* __restrict__ tile_occ, int b, int y, int x, int H, int W) {
+    const int tiles_y = (H + SASSD_CONV2D_TILE_H - 1) / SASSD_CONV2D_TILE_H;
+    const int tiles_x = (W + SASSD_CONV2D_TILE_W - 1) / SASSD_CONV2D_TILE_W;
+    const int ty0 = max(y - 1, 0) / SASSD_CONV2D_TILE_H, ty1 = min(y + 1, H - 1) / SASSD_CONV2D_TILE_H;
+    const int tx0 = max(x - 1, 0) / SASSD_CONV2D_TILE_W, tx1 = min(x + 1, W - 1) / SASSD_CONV2D_TILE_W;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) tile_occ[(b * tiles_y + ty) * tiles_x + tx] = 1;
+}
+
 __device__ __forceinline__ uint32_t sassd_hash32(uint32_t k) {
     // Fibonacci hashing followed by a xor-fold; table sizes are powers of two.
     k *= 0x9E3779B1u;

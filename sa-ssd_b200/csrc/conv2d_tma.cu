@@ -26,7 +26,7 @@ namespace tma {
 
 using namespace tc;
 
-constexpr int TILE_H = 8, TILE_W = 16;          // 128 output pixels per tile
+constexpr int TILE_H = SASSD_CONV2D_TILE_H, TILE_W = SASSD_CONV2D_TILE_W;   // 8 x 16 = 128 output pixels per tile
 constexpr int BKC = 64;                         // channels per chunk (one 128-byte fp16 row)
 constexpr int EPI_WARPS = 4;
 constexpr int THREADS2 = (EPI_WARPS + 2) * 32;  // 192
@@ -71,6 +71,7 @@ struct Conv2dArgs {
     float* out_f32;       // [B,H,W,out_f32_stride] or null
     __half* out_split;    // [2,B,H,W,out_split_ch] or null
     int batch, H, W, cin, cout, taps, relu, out_f32_stride, out_split_ch;
+    const int* tile_occ;  // optional: 0 = the tile and its halo are all-zero input (skip the main loop)
     int dbg;              // SASSD_TMA_DBG (timing experiments only): 1 = reuse stale B stages, 2 = reuse stale A stages,
                           // 4 = plain MMAs (no operand collector)
 };
@@ -83,7 +84,7 @@ struct Conv2dArgs {
 template <int BN, class Release>
 __device__ __forceinline__ void drain_tile(const Conv2dArgs& p, const CUtensorMap* omap, uint32_t tmem_acc, int warp,
                                            int lane, int b, int ty, int tx, bool store, uint32_t my_stage,
-                                           uint32_t& store_it, Release&& release) {
+                                           uint32_t& store_it, Release&& release, bool zero_acc = false) {
     const int r = warp * 32 + lane;
     const int py = r / TILE_W, px = r % TILE_W;
     const int y = ty * TILE_H + py, x = tx * TILE_W + px;
@@ -96,13 +97,18 @@ __device__ __forceinline__ void drain_tile(const Conv2dArgs& p, const CUtensorMa
     for (int c0 = 0; c0 < BN; c0 += CW) {
         uint32_t v[CW], u[CW];
         const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        tmem_ld<CW>(v, taddr);
-        tmem_ld<CW>(u, taddr + (uint32_t)BN);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + CW >= BN) {      // accumulators are in registers: the next tile's MMAs may start
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release();
+        if (zero_acc) {           // all-zero input tile: the accumulators would be exactly 0
+#pragma unroll
+            for (int j = 0; j < CW; ++j) { v[j] = 0u; u[j] = 0u; }
+        } else {
+            tmem_ld<CW>(v, taddr);
+            tmem_ld<CW>(u, taddr + (uint32_t)BN);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 + CW >= BN) {      // accumulators are in registers: the next tile's MMAs may start
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) release();
+            }
         }
         float o[CW];
 #pragma unroll
@@ -226,6 +232,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             int stage = 0, issued = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (p.tile_occ && __ldg(&p.tile_occ[tile]) == 0) continue;      // all-zero input: nothing to load
                 const int b = tile / (tiles_y * tiles_x);
                 const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
                 const int y0 = ty * TILE_H, x0 = tx * TILE_W;
@@ -264,6 +271,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (p.tile_occ && __ldg(&p.tile_occ[tile]) == 0) continue;      // the epilogue stores act(shift)
                 mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
@@ -311,6 +319,10 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / (tiles_y * tiles_x);
             const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
+            if (p.tile_occ && __ldg(&p.tile_occ[tile]) == 0) {      // no MMAs ran for this tile: zero accumulators
+                drain_tile<BN>(p, &omap, 0u, warp, lane, b, ty, tx, true, my_stage, store_it, [] {}, true);
+                continue;
+            }
             if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
             __syncwarp();
             tc_fence_after();
@@ -570,6 +582,12 @@ static int launch2(const CUtensorMap& map, const CUtensorMap& omap, const Conv2d
 extern "C" int sassd_conv2d_f16x3(const sassd_conv2d_desc* d, const void* in_split, const void* wpack,
                                   const float* scale, const float* shift, float* out_f32, void* out_split,
                                   sassd_stream_t stream_) {
+    return sassd_conv2d_f16x3_occ(d, in_split, wpack, scale, shift, out_f32, out_split, nullptr, stream_);
+}
+
+extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in_split, const void* wpack,
+                                      const float* scale, const float* shift, float* out_f32, void* out_split,
+                                      const int32_t* tile_occ, sassd_stream_t stream_) {
     using namespace tma;
     if (!d || !in_split || !wpack || (!out_f32 && !out_split)) return SASSD_ERR_ARG;
     if (d->batch < 1 || d->H < 1 || d->W < 1 || d->cin < 1 || d->cout < 1 || d->cout > 256) return SASSD_ERR_ARG;
@@ -593,6 +611,7 @@ extern "C" int sassd_conv2d_f16x3(const sassd_conv2d_desc* d, const void* in_spl
     a.wpack = wpack; a.scale = scale; a.shift = shift; a.out_f32 = out_f32; a.out_split = (__half*)out_split;
     a.batch = d->batch; a.H = d->H; a.W = d->W; a.cin = d->cin; a.cout = d->cout; a.taps = d->taps; a.relu = d->relu;
     a.out_f32_stride = d->out_f32_stride; a.out_split_ch = d->out_split_ch;
+    a.tile_occ = tile_occ;
     static const int dbg = [] { const char* e = getenv("SASSD_TMA_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -650,7 +669,7 @@ extern "C" int sassd_conv2d_f16x3(const sassd_conv2d_desc* d, const void* in_spl
 // SparseConvTensor.dense() into the split BEV map: hi / lo*2048 fp16 planes [2,B,H,W,D*C] (channel d*C + c).
 __global__ void sparse_to_bev_split_kernel(const float4* __restrict__ feat, const int4* __restrict__ coors,
                                            const int* __restrict__ d_rows, int rows_cap, int C4, int D, int H, int W,
-                                           size_t plane, __half* __restrict__ bev) {
+                                           size_t plane, __half* __restrict__ bev, int* __restrict__ tile_occ) {
     const int rows = min(*d_rows, rows_cap);
     const long long total = (long long)rows * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -664,15 +683,17 @@ __global__ void sparse_to_bev_split_kernel(const float4* __restrict__ feat, cons
         __half* dst = bev + ((((size_t)c.x * H + c.z) * W + c.w) * (size_t)(D * C4) + (size_t)c.y * C4 + q) * 4;
         *(uint2*)dst = make_uint2(h0, h1);
         *(uint2*)(dst + plane) = make_uint2(l0, l1);
+        if (tile_occ && q == 0) sassd_mark_conv2d_tiles(tile_occ, c.x, c.z, c.w, H, W);
     }
 }
 
 extern "C" int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap,
-                                         int C, int D, int H, int W, int batch, void* bev_split, sassd_stream_t stream_) {
+                                         int C, int D, int H, int W, int batch, void* bev_split, int32_t* tile_occ,
+                                         sassd_stream_t stream_) {
     if (!feat || !coors || !d_rows || !bev_split || (C & 3) || batch < 1) return SASSD_ERR_ARG;
     if (rows_cap <= 0) return SASSD_OK;
     const size_t plane = (size_t)batch * H * W * D * C;
     sparse_to_bev_split_kernel<<<sassd_grid((long long)rows_cap * (C / 4), 256), 256, 0, (cudaStream_t)stream_>>>(
-        (const float4*)feat, (const int4*)coors, d_rows, rows_cap, C / 4, D, H, W, plane, (__half*)bev_split);
+        (const float4*)feat, (const int4*)coors, d_rows, rows_cap, C / 4, D, H, W, plane, (__half*)bev_split, tile_occ);
     return sassd_check_launch();
 }

@@ -33,6 +33,7 @@ class GConvDesc(ctypes.Structure):
 
 GCONV_TABLE, GCONV_CONV2D, GCONV_ROWS = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2
+CONV2D_TILE_H, CONV2D_TILE_W = 8, 16      # SASSD_CONV2D_TILE_H / _W of the header
 
 OK = 0
 ERRORS = {-1: "SASSD_ERR_ARG", -2: "SASSD_ERR_LAUNCH", -3: "SASSD_ERR_WORKSPACE", -4: "SASSD_ERR_UNSUPPORTED"}
@@ -57,6 +58,7 @@ _SIGNATURES = {
     "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_gconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "sassd_conv2d_f16x3": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P]),
+    "sassd_conv2d_f16x3_occ": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P, P]),
     "sassd_rotate_overlap_eval": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P]),
     "sassd_kitti_match": (c_int, [c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_int, ctypes.c_double, c_int, c_int, P, P,
                                   P, P]),
@@ -64,8 +66,8 @@ _SIGNATURES = {
     "sassd_spconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "sassd_spconv_f16x3": (c_int, [ctypes.POINTER(SpconvDesc), P, P, P, P, P, P, P, P, P]),
     "sassd_features_to_split": (c_int, [P, P, c_int, c_int, c_int, P, P]),
-    "sassd_split_rows_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
-    "sassd_sparse_to_bev_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "sassd_split_rows_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    "sassd_sparse_to_bev_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, c_int, P,

@@ -6,6 +6,7 @@ current torch stream and keep data-dependent sizes on the device (``d_rows``
 style int32 tensors) — nothing in this module synchronises.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -47,7 +48,7 @@ def next_pow2(n):
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
             "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
-            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_spconv_pack": 1, "sassd_rotate_overlap_eval": 1, "sassd_conv2d_f16x3": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
+            "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_spconv_pack": 1, "sassd_rotate_overlap_eval": 1, "sassd_conv2d_f16x3": 1, "sassd_conv2d_f16x3_occ": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
 LAUNCHES = 0          # running count of kernels launched through this module
@@ -337,8 +338,10 @@ class SplitMap:
     """Activation map as two fp16 planes [2, B, H, W, C_stored] (hi, lo*2048) — the operand format of
     sassd_conv2d_f16x3; ``channels`` of the C_stored are meaningful, the rest are zero."""
 
-    def __init__(self, planes, channels):
-        self.planes, self.channels = planes, channels
+    def __init__(self, planes, channels, tile_occ=None):
+        # tile_occ: optional int32 [B * tiles_y * tiles_x] flags of the conv tiles whose input is not all zero
+        # (maps scattered from a sparse tensor carry it; conv2d_split then skips the empty tiles)
+        self.planes, self.channels, self.tile_occ = planes, channels, tile_occ
 
     @property
     def shape(self):
@@ -365,11 +368,22 @@ class SplitMap:
         return SplitMap(planes, C)
 
 
+TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # sparse-aware first BEV conv (0: compute every tile)
+
+
+def _tile_flags(batch, H, W, device):
+    if not TILE_OCCUPANCY:
+        return None
+    th, tw = _lib.CONV2D_TILE_H, _lib.CONV2D_TILE_W
+    return torch.zeros((batch * ((H + th - 1) // th) * ((W + tw - 1) // tw),), dtype=torch.int32, device=device)
+
+
 def sparse_to_bev_split(feat, coors, d_rows, C, D, H, W, batch):
     planes = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=feat.device)
+    occ = _tile_flags(batch, H, W, feat.device)
     _call("sassd_sparse_to_bev_split", None, _ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, batch,
-          _ptr(planes), _stream())
-    return SplitMap(planes, D * C)
+          _ptr(planes), _ptr(occ), _stream())
+    return SplitMap(planes, D * C, occ)
 
 
 def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=False):
@@ -392,8 +406,8 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
         of = torch.empty((B, H, W, stride), dtype=torch.float32, device=x.device)
         d.out_f32_stride = stride
     label = "conv2d_tma[taps=%d %d->%d]" % (taps, cin, cout)
-    _call("sassd_conv2d_f16x3", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
-          _ptr(osp), _stream())
+    _call("sassd_conv2d_f16x3_occ", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
+          _ptr(osp), _ptr(x.tile_occ), _stream())
     return (SplitMap(osp, cout) if osp is not None else None), of
 
 
@@ -434,6 +448,7 @@ def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d
 
 def split_rows_to_bev(planes, coors, d_rows, C, D, H, W, batch):
     bev = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=planes.device)
+    occ = _tile_flags(batch, H, W, planes.device)
     _call("sassd_split_rows_to_bev", None, _ptr(planes), _ptr(coors), _ptr(d_rows), planes.shape[1], C, D, H, W, batch,
-          _ptr(bev), _stream())
-    return SplitMap(bev, D * C)
+          _ptr(bev), _ptr(occ), _stream())
+    return SplitMap(bev, D * C, occ)

@@ -596,3 +596,42 @@ def test_tcgen05_kernel_unit_checks(stage, env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout, r.stdout[-3000:]
     assert r.stdout.count(" OK") >= 7, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taps,cout", [(9, 256), (9, 28), (1, 256)])
+def test_sparse_aware_conv_tiles_are_bit_identical(dev, taps, cout):
+    """A scattered (mostly zero) BEV map carries per-tile occupancy flags; tiles flagged empty skip the main loop and
+    store act(shift).  Must equal the all-tiles computation bit for bit, including frames with no active cell."""
+    from sassd_b200 import ops
+    torch.manual_seed(taps * 100 + cout)
+    B, H, W, C, D = 3, 40, 52, 64, 2
+    n = 40
+    coors = torch.zeros((64, 4), dtype=torch.int32, device=dev)
+    coors[:n, 0] = torch.randint(0, 2, (n,), device=dev)           # frame 2 stays empty
+    coors[:n, 1] = torch.randint(0, D, (n,), device=dev)
+    coors[:n, 2] = torch.randint(0, 12, (n,), device=dev)          # active cells clustered in a corner ...
+    coors[:n, 3] = torch.randint(0, 20, (n,), device=dev)
+    coors[n - 1, 2], coors[n - 1, 3] = H - 1, W - 1                  # ... plus one in the far corner
+    key = ((coors[:n, 0].long() * D + coors[:n, 1].long()) * H + coors[:n, 2].long()) * W + coors[:n, 3].long()
+    keep = torch.from_numpy(np.unique(key.cpu().numpy(), return_index=True)[1]).to(dev)
+    rows = coors[keep].contiguous()
+    n = rows.shape[0]
+    cap = torch.zeros((64, 4), dtype=torch.int32, device=dev)
+    cap[:n] = rows
+    feat = torch.randn(64, C, device=dev)
+    d_rows = torch.tensor([n], dtype=torch.int32, device=dev)
+    x = ops.sparse_to_bev_split(feat, cap, d_rows, C, D, H, W, B)
+    assert x.tile_occ is not None and 0 < int(x.tile_occ.sum()) < x.tile_occ.numel()
+    w = torch.randn(taps, D * C, cout, device=dev) * 0.1
+    scale = torch.rand(cout, device=dev) + 0.5
+    shift = torch.randn(cout, device=dev) * 0.3
+    sp_occ, f_occ = ops.conv2d_split(x, w, scale, shift, True, cout, out_split=True, out_f32=True)
+    full = ops.SplitMap(x.planes, x.channels)                        # same map without the flags
+    sp_all, f_all = ops.conv2d_split(full, w, scale, shift, True, cout, out_split=True, out_f32=True)
+    torch.cuda.synchronize()
+    assert torch.equal(f_occ[..., :cout], f_all[..., :cout])
+    assert torch.equal(sp_occ.planes, sp_all.planes)
+    # empty tiles hold exactly act(shift)
+    const = torch.relu(shift)
+    assert torch.equal(f_occ[2, H // 2, W // 2, :cout], const)
