@@ -172,19 +172,25 @@ typedef struct {
 } sassd_conv2d_desc;
 int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
                        const float* shift, float* out_f32, void* out_split, sassd_stream_t stream);
-/* Same, for an input that is mostly zero (the scattered sparse tensor): tile_occ[(b * tiles_y + ty) * tiles_x + tx]
- * != 0 iff the SASSD_CONV2D_TILE_H x SASSD_CONV2D_TILE_W pixel tile or its one-pixel halo holds an active cell
- * (written by sassd_split_rows_to_bev / sassd_sparse_to_bev_split).  Tiles whose flag is 0 skip the main loop and
- * store act(shift) directly - bit-identical to multiplying the zeros.  tile_occ == NULL: plain sassd_conv2d_f16x3. */
+/* Same, for maps that descend from a scattered sparse tensor and are therefore constant over large regions.
+ * tile_dist[(b * tiles_y + ty) * tiles_x + tx] (written by sassd_split_rows_to_bev / sassd_sparse_to_bev_split into a
+ * buffer pre-filled with a large value) is the Chebyshev distance in pixels from the SASSD_CONV2D_TILE_H x
+ * SASSD_CONV2D_TILE_W tile to the nearest active cell of the scattered map.  `reach` = number of 3x3 convolutions
+ * between that map and this layer's OUTPUT (1 for the first conv): a tile with tile_dist > reach that does not lie on
+ * the image border (border tiles are always computed once reach >= 2, because the zero padding differs from the
+ * constant) sees a constant input, so its output is the constant vector `const_out[cout]` (the caller obtains it by
+ * running this same function on a small constant map - bit-identical to computing the tile).  Such tiles skip loads
+ * and MMAs and only store.  tile_dist == NULL: plain sassd_conv2d_f16x3. */
 #define SASSD_CONV2D_TILE_H 8
 #define SASSD_CONV2D_TILE_W 16
+#define SASSD_TILE_DIST_MAX 9          /* distances beyond this are stored as any larger value */
 int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack,
                            const float* scale, const float* shift, float* out_f32, void* out_split,
-                           const int32_t* tile_occ, sassd_stream_t stream);
+                           const int32_t* tile_dist, int reach, const float* const_out, sassd_stream_t stream);
 /* dense() of the last sparse tensor straight into a (pre-zeroed) split map [2,batch,H,W,D*C]. */
 int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
-                              int D, int H, int W, int batch, void* bev_split, int32_t* tile_occ,
-                              sassd_stream_t stream);   /* tile_occ: optional (pre-zeroed) tile flags, see above */
+                              int D, int H, int W, int batch, void* bev_split, int32_t* tile_dist,
+                              sassd_stream_t stream);   /* tile_dist: optional, pre-filled with a large value, see above */
 
 /* Ruled sparse conv on "split rows" (two fp16 planes [2][rows][C], C % 8 == 0; hi = half(x), lo = half((x-hi)*2048)):
  * same semantics as sassd_gconv TABLE / ROWS mode with SASSD_PREC_F16X3, but the gather is 16-byte cp.async copies
@@ -208,8 +214,8 @@ int sassd_features_to_split(const float* feat, const int32_t* d_rows, int rows_c
                             sassd_stream_t stream);
 /* dense() of split rows into a (pre-zeroed) split BEV map [2,batch,H,W,D*C]. */
 int sassd_split_rows_to_bev(const void* feat_split, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
-                            int D, int H, int W, int batch, void* bev_split, int32_t* tile_occ, sassd_stream_t stream);
-                            /* tile_occ: optional (pre-zeroed) tile flags for sassd_conv2d_f16x3_occ */
+                            int D, int H, int W, int batch, void* bev_split, int32_t* tile_dist, sassd_stream_t stream);
+                            /* tile_dist: optional, pre-filled with a large value (sassd_conv2d_f16x3_occ) */
 
 /* SparseConvTensor.dense() + view (cmn.py:112-114) into the NHWC BEV map the
  * neck consumes: bev[b, y, x, d*C + c] = feat[row, c]  (reference channel c*D+d;

@@ -24,15 +24,21 @@ static inline int sassd_grid(long long work, int block, int ctas_per_sm = 8) {
     return (int)(need < cap ? need : cap);
 }
 
-// An active BEV cell (b, y, x) marks every SASSD_CONV2D_TILE_H x SASSD_CONV2D_TILE_W tile that contains it or has it
-// in its one-pixel halo (sassd_conv2d_f16x3_occ skips the tiles left at 0).  Plain stores of 1: races are benign.
-__device__ __forceinline__ void sassd_mark_conv2d_tiles(int* __restrict__ tile_occ, int b, int y, int x, int H, int W) {
+// An active BEV cell (b, y, x) lowers tile_dist of every conv tile within SASSD_TILE_DIST_MAX pixels to its Chebyshev
+// distance from the tile rectangle (0 inside the tile).  sassd_conv2d_f16x3_occ compares it with the layer's reach.
+__device__ __forceinline__ void sassd_mark_conv2d_tiles(int* __restrict__ tile_dist, int b, int y, int x, int H, int W) {
     const int tiles_y = (H + SASSD_CONV2D_TILE_H - 1) / SASSD_CONV2D_TILE_H;
     const int tiles_x = (W + SASSD_CONV2D_TILE_W - 1) / SASSD_CONV2D_TILE_W;
-    const int ty0 = max(y - 1, 0) / SASSD_CONV2D_TILE_H, ty1 = min(y + 1, H - 1) / SASSD_CONV2D_TILE_H;
-    const int tx0 = max(x - 1, 0) / SASSD_CONV2D_TILE_W, tx1 = min(x + 1, W - 1) / SASSD_CONV2D_TILE_W;
+    const int R = SASSD_TILE_DIST_MAX;
+    const int ty0 = max(y - R, 0) / SASSD_CONV2D_TILE_H, ty1 = min(y + R, H - 1) / SASSD_CONV2D_TILE_H;
+    const int tx0 = max(x - R, 0) / SASSD_CONV2D_TILE_W, tx1 = min(x + R, W - 1) / SASSD_CONV2D_TILE_W;
     for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) tile_occ[(b * tiles_y + ty) * tiles_x + tx] = 1;
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int y0 = ty * SASSD_CONV2D_TILE_H, x0 = tx * SASSD_CONV2D_TILE_W;
+            const int dy = max(max(y0 - y, y - (y0 + SASSD_CONV2D_TILE_H - 1)), 0);
+            const int dx = max(max(x0 - x, x - (x0 + SASSD_CONV2D_TILE_W - 1)), 0);
+            atomicMin(&tile_dist[(b * tiles_y + ty) * tiles_x + tx], max(dy, dx));
+        }
 }
 
 __device__ __forceinline__ uint32_t sassd_hash32(uint32_t k) {

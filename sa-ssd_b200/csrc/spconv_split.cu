@@ -531,7 +531,7 @@ extern "C" int sassd_features_to_split(const float* feat, const int32_t* d_rows,
 // dense(): split rows [2][rows_cap][C] -> split BEV map [2][B][H][W][D*C] (channel d*C + c), 16 bytes per thread
 __global__ void split_rows_to_bev_kernel(const uint4* __restrict__ feat, size_t in_plane16, const int4* __restrict__ coors,
                                          const int* __restrict__ d_rows, int rows_cap, int C8, int D, int H, int W,
-                                         size_t out_plane16, uint4* __restrict__ bev, int* __restrict__ tile_occ) {
+                                         size_t out_plane16, uint4* __restrict__ bev, int* __restrict__ tile_dist) {
     const int rows = min(*d_rows, rows_cap);
     const long long total = (long long)rows * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -540,18 +540,18 @@ __global__ void split_rows_to_bev_kernel(const uint4* __restrict__ feat, size_t 
         const size_t o = (((size_t)c.x * H + c.z) * W + c.w) * (size_t)(D * C8) + (size_t)c.y * C8 + q;
         bev[o] = __ldg(&feat[i]);
         bev[o + out_plane16] = __ldg(&feat[i + in_plane16]);
-        if (tile_occ && q == 0) sassd_mark_conv2d_tiles(tile_occ, c.x, c.z, c.w, H, W);
+        if (tile_dist && q == 0) sassd_mark_conv2d_tiles(tile_dist, c.x, c.z, c.w, H, W);
     }
 }
 
 extern "C" int sassd_split_rows_to_bev(const void* feat_split, const int32_t* coors, const int32_t* d_rows, int rows_cap,
-                                       int C, int D, int H, int W, int batch, void* bev_split, int32_t* tile_occ,
+                                       int C, int D, int H, int W, int batch, void* bev_split, int32_t* tile_dist,
                                        sassd_stream_t stream_) {
     if (!feat_split || !coors || !d_rows || !bev_split || (C & 7) || batch < 1) return SASSD_ERR_ARG;
     if (rows_cap <= 0) return SASSD_OK;
     const size_t in_plane16 = (size_t)rows_cap * C / 8, out_plane16 = (size_t)batch * H * W * D * C / 8;
     split_rows_to_bev_kernel<<<sassd_grid((long long)rows_cap * (C / 8), 256), 256, 0, (cudaStream_t)stream_>>>(
         (const uint4*)feat_split, in_plane16, (const int4*)coors, d_rows, rows_cap, C / 8, D, H, W, out_plane16,
-        (uint4*)bev_split, tile_occ);
+        (uint4*)bev_split, tile_dist);
     return sassd_check_launch();
 }

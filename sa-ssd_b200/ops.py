@@ -338,10 +338,13 @@ class SplitMap:
     """Activation map as two fp16 planes [2, B, H, W, C_stored] (hi, lo*2048) — the operand format of
     sassd_conv2d_f16x3; ``channels`` of the C_stored are meaningful, the rest are zero."""
 
-    def __init__(self, planes, channels, tile_occ=None):
-        # tile_occ: optional int32 [B * tiles_y * tiles_x] flags of the conv tiles whose input is not all zero
-        # (maps scattered from a sparse tensor carry it; conv2d_split then skips the empty tiles)
-        self.planes, self.channels, self.tile_occ = planes, channels, tile_occ
+    def __init__(self, planes, channels, tile_dist=None, reach=0, const=None):
+        # Maps that descend from a scattered sparse tensor are constant over large regions.  tile_dist: int32
+        # [B * tiles_y * tiles_x], pixel distance of every conv tile to the nearest active cell of the scattered map;
+        # reach: number of 3x3 convs applied since; const: fp32 [channels] value of the constant region (None = 0).
+        # conv2d_split uses them to skip the tiles whose output is the layer's constant (see sassd_conv2d_f16x3_occ).
+        self.planes, self.channels = planes, channels
+        self.tile_dist, self.reach, self.const = tile_dist, reach, const
 
     @property
     def shape(self):
@@ -368,22 +371,47 @@ class SplitMap:
         return SplitMap(planes, C)
 
 
-TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # sparse-aware first BEV conv (0: compute every tile)
+TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # constant-region tile skipping in the BEV convs
+_TILE_FAR = 1 << 20
 
 
-def _tile_flags(batch, H, W, device):
+def _tile_dist(batch, H, W, device):
     if not TILE_OCCUPANCY:
         return None
     th, tw = _lib.CONV2D_TILE_H, _lib.CONV2D_TILE_W
-    return torch.zeros((batch * ((H + th - 1) // th) * ((W + tw - 1) // tw),), dtype=torch.int32, device=device)
+    return torch.full((batch * ((H + th - 1) // th) * ((W + tw - 1) // tw),), _TILE_FAR, dtype=torch.int32, device=device)
+
+
+_CONV_CONSTS = {}
+
+
+def conv_constant(x_const, cin, weight, scale, shift, relu, cout):
+    """Output of a conv layer on a constant input map: fp32 [cout], obtained by running the very kernel on a
+    3x3-tile map filled with the constant and reading an interior pixel, so tiles that skip the computation store
+    bit-identical values.  Depends on weights only (cached; warm before CUDA-graph capture)."""
+    key = (weight.data_ptr(), weight._version, None if scale is None else (scale.data_ptr(), scale._version),
+           None if shift is None else (shift.data_ptr(), shift._version), bool(relu), cout, cin,
+           None if x_const is None else x_const.data_ptr())
+    ent = _CONV_CONSTS.get(key)
+    if ent is None:
+        if len(_CONV_CONSTS) >= 256:
+            _CONV_CONSTS.pop(next(iter(_CONV_CONSTS)))
+        h, w = 3 * _lib.CONV2D_TILE_H, 3 * _lib.CONV2D_TILE_W
+        m = torch.zeros((1, h, w, cin), dtype=torch.float32, device=weight.device)
+        if x_const is not None:
+            m += x_const[:cin].view(1, 1, 1, cin)
+        _, f = conv2d_split(SplitMap.from_float(m), weight, scale, shift, relu, cout, out_split=False, out_f32=True)
+        ent = (f[0, h // 2, w // 2, :cout].clone().contiguous(), weight, scale, shift, x_const)   # keep keys alive
+        _CONV_CONSTS[key] = ent
+    return ent[0]
 
 
 def sparse_to_bev_split(feat, coors, d_rows, C, D, H, W, batch):
     planes = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=feat.device)
-    occ = _tile_flags(batch, H, W, feat.device)
+    dist = _tile_dist(batch, H, W, feat.device)
     _call("sassd_sparse_to_bev_split", None, _ptr(feat), _ptr(coors), _ptr(d_rows), feat.shape[0], C, D, H, W, batch,
-          _ptr(planes), _ptr(occ), _stream())
-    return SplitMap(planes, D * C, occ)
+          _ptr(planes), _ptr(dist), _stream())
+    return SplitMap(planes, D * C, dist)
 
 
 def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=False):
@@ -406,9 +434,14 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
         of = torch.empty((B, H, W, stride), dtype=torch.float32, device=x.device)
         d.out_f32_stride = stride
     label = "conv2d_tma[taps=%d %d->%d]" % (taps, cin, cout)
+    dist = x.tile_dist if TILE_OCCUPANCY else None
+    reach, cvec = 0, None
+    if dist is not None:
+        reach = x.reach + (1 if taps == 9 else 0)
+        cvec = conv_constant(x.const, cin, weight, scale, shift, relu, cout)
     _call("sassd_conv2d_f16x3_occ", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
-          _ptr(osp), _ptr(x.tile_occ), _stream())
-    return (SplitMap(osp, cout) if osp is not None else None), of
+          _ptr(osp), _ptr(dist), reach, _ptr(cvec), _stream())
+    return (SplitMap(osp, cout, dist, reach, cvec) if osp is not None else None), of
 
 
 # ---------------------------------------------------------------------------- sparse conv on split rows
@@ -448,7 +481,7 @@ def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d
 
 def split_rows_to_bev(planes, coors, d_rows, C, D, H, W, batch):
     bev = torch.zeros((2, batch, H, W, D * C), dtype=torch.float16, device=planes.device)
-    occ = _tile_flags(batch, H, W, planes.device)
+    dist = _tile_dist(batch, H, W, planes.device)
     _call("sassd_split_rows_to_bev", None, _ptr(planes), _ptr(coors), _ptr(d_rows), planes.shape[1], C, D, H, W, batch,
-          _ptr(bev), _ptr(occ), _stream())
-    return SplitMap(bev, D * C, occ)
+          _ptr(bev), _ptr(dist), _stream())
+    return SplitMap(bev, D * C, dist)

@@ -598,40 +598,98 @@ def test_tcgen05_kernel_unit_checks(stage, env):
     assert r.stdout.count(" OK") >= 7, r.stdout[-3000:]
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("taps,cout", [(9, 256), (9, 28), (1, 256)])
-def test_sparse_aware_conv_tiles_are_bit_identical(dev, taps, cout):
-    """A scattered (mostly zero) BEV map carries per-tile occupancy flags; tiles flagged empty skip the main loop and
-    store act(shift).  Must equal the all-tiles computation bit for bit, including frames with no active cell."""
+def _scattered_map(dev, B, H, W, C, D, seed):
     from sassd_b200 import ops
-    torch.manual_seed(taps * 100 + cout)
-    B, H, W, C, D = 3, 40, 52, 64, 2
+    torch.manual_seed(seed)
     n = 40
-    coors = torch.zeros((64, 4), dtype=torch.int32, device=dev)
-    coors[:n, 0] = torch.randint(0, 2, (n,), device=dev)           # frame 2 stays empty
-    coors[:n, 1] = torch.randint(0, D, (n,), device=dev)
-    coors[:n, 2] = torch.randint(0, 12, (n,), device=dev)          # active cells clustered in a corner ...
-    coors[:n, 3] = torch.randint(0, 20, (n,), device=dev)
-    coors[n - 1, 2], coors[n - 1, 3] = H - 1, W - 1                  # ... plus one in the far corner
-    key = ((coors[:n, 0].long() * D + coors[:n, 1].long()) * H + coors[:n, 2].long()) * W + coors[:n, 3].long()
+    coors = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+    coors[:, 0] = torch.randint(0, max(B - 1, 1), (n,), device=dev)      # the last frame stays empty
+    coors[:, 1] = torch.randint(0, D, (n,), device=dev)
+    coors[:, 2] = torch.randint(0, 12, (n,), device=dev)                 # active cells clustered in a corner ...
+    coors[:, 3] = torch.randint(0, 20, (n,), device=dev)
+    coors[n - 1, 2], coors[n - 1, 3] = H - 1, W - 1                      # ... plus one in the far corner
+    key = ((coors[:, 0].long() * D + coors[:, 1].long()) * H + coors[:, 2].long()) * W + coors[:, 3].long()
     keep = torch.from_numpy(np.unique(key.cpu().numpy(), return_index=True)[1]).to(dev)
     rows = coors[keep].contiguous()
-    n = rows.shape[0]
     cap = torch.zeros((64, 4), dtype=torch.int32, device=dev)
-    cap[:n] = rows
+    cap[: rows.shape[0]] = rows
     feat = torch.randn(64, C, device=dev)
-    d_rows = torch.tensor([n], dtype=torch.int32, device=dev)
-    x = ops.sparse_to_bev_split(feat, cap, d_rows, C, D, H, W, B)
-    assert x.tile_occ is not None and 0 < int(x.tile_occ.sum()) < x.tile_occ.numel()
+    d_rows = torch.tensor([rows.shape[0]], dtype=torch.int32, device=dev)
+    return ops.sparse_to_bev_split(feat, cap, d_rows, C, D, H, W, B)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taps,cout", [(9, 256), (9, 28), (1, 256)])
+def test_constant_tiles_single_layer_bit_identical(dev, taps, cout):
+    """A scattered (mostly zero) BEV map carries per-tile distances to its active cells; tiles out of the layer's
+    reach skip loads and MMAs and store the layer's constant.  Must equal the all-tiles computation bit for bit,
+    including a frame with no active cell."""
+    from sassd_b200 import ops
+    B, H, W, C, D = 3, 40, 52, 64, 2
+    x = _scattered_map(dev, B, H, W, C, D, taps * 100 + cout)
+    far = (x.tile_dist > 9).sum().item()
+    assert x.tile_dist is not None and 0 < far < x.tile_dist.numel()
     w = torch.randn(taps, D * C, cout, device=dev) * 0.1
     scale = torch.rand(cout, device=dev) + 0.5
     shift = torch.randn(cout, device=dev) * 0.3
     sp_occ, f_occ = ops.conv2d_split(x, w, scale, shift, True, cout, out_split=True, out_f32=True)
-    full = ops.SplitMap(x.planes, x.channels)                        # same map without the flags
+    full = ops.SplitMap(x.planes, x.channels)                        # same map without the tile information
     sp_all, f_all = ops.conv2d_split(full, w, scale, shift, True, cout, out_split=True, out_f32=True)
     torch.cuda.synchronize()
     assert torch.equal(f_occ[..., :cout], f_all[..., :cout])
     assert torch.equal(sp_occ.planes, sp_all.planes)
-    # empty tiles hold exactly act(shift)
-    const = torch.relu(shift)
-    assert torch.equal(f_occ[2, H // 2, W // 2, :cout], const)
+    assert torch.equal(f_occ[B - 1, H // 2, W // 2, :cout], torch.relu(shift))      # empty frame: act(shift)
+
+
+@pytest.mark.gpu
+def test_constant_tiles_through_a_layer_chain_bit_identical(dev):
+    """3x3 -> 3x3 -> 3x3 -> 1x1 -> 3x3 (small head): constants, reach and the border rule (zero padding differs from
+    the constant) must reproduce the plain computation exactly at every layer."""
+    from sassd_b200 import ops
+    B, H, W, C, D = 2, 56, 80, 64, 1
+    torch.manual_seed(5)
+    layers = [(9, 64, 64), (9, 64, 64), (9, 64, 64), (1, 64, 64), (9, 64, 28)]
+    params = [(torch.randn(t, ci, co, device=dev) * (0.3 / (t * ci) ** 0.5 * 4), torch.rand(co, device=dev) + 0.5,
+               torch.randn(co, device=dev) * 0.3) for t, ci, co in layers]
+
+    def run(use_tiles):
+        ops.TILE_OCCUPANCY = use_tiles
+        try:
+            x = _scattered_map(dev, B, H, W, C, D, 77)
+            outs = []
+            for (t, ci, co), (w, sc, sh) in zip(layers, params):
+                x, f = ops.conv2d_split(x, w, sc, sh, True, co, out_split=True, out_f32=True)
+                outs.append((x.planes.clone(), f.clone(), x.reach))
+            torch.cuda.synchronize()
+            return outs
+        finally:
+            ops.TILE_OCCUPANCY = True
+    with_tiles, plain = run(True), run(False)
+    assert [o[2] for o in with_tiles] == [1, 2, 3, 3, 4]
+    for i, (a, b) in enumerate(zip(with_tiles, plain)):
+        assert torch.equal(a[0], b[0]), "split planes differ at layer %d" % i
+        assert torch.equal(a[1], b[1]), "fp32 map differs at layer %d" % i
+
+
+@pytest.mark.gpu
+def test_constant_tile_skipping_leaves_detections_unchanged(dev):
+    """Whole pipeline with and without the constant-region tile skipping: identical detections, bit for bit."""
+    from sassd_b200 import ops
+    model, sd = _make_model(dev)
+    frames = [[synth_cloud(s)] for s in (0, 9, 3)] + [[synth_cloud(1), synth_cloud(7)]]
+    res = {}
+    for flag in (True, False):
+        ops.TILE_OCCUPANCY = flag
+        try:
+            res[flag] = [model.forward_points(f) for f in frames]
+        finally:
+            ops.TILE_OCCUPANCY = True
+    ndet = 0
+    for a, b in zip(res[True], res[False]):
+        for fa, fb in zip(a, b):
+            assert (fa["boxes_lidar"] is None) == (fb["boxes_lidar"] is None)
+            if fa["boxes_lidar"] is not None:
+                np.testing.assert_array_equal(fa["boxes_lidar"], fb["boxes_lidar"])
+                np.testing.assert_array_equal(fa["scores"], fb["scores"])
+                ndet += len(fa["scores"])
+    assert ndet > 0
