@@ -20,7 +20,6 @@ Pinning status:
     the GPU box the unmodified reference kernel built into oracle/_ref/.
 """
 import ctypes
-import math
 import os
 
 import numpy as np

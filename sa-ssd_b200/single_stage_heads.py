@@ -5,7 +5,6 @@ PSWarpHead (mmdet/models/single_stage_heads/ssd_rotate_head.py:95-125,218-235,
 
 Inference methods only; ``loss`` / target assignment are training code and out of scope.
 """
-from functools import partial
 
 import numpy as np
 import torch
