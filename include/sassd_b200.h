@@ -46,7 +46,8 @@ enum { /* bits of *d_status */
     SASSD_FLAG_ROWS_CAP = 2,    /* strided-conv output rows exceed capacity */
     SASSD_FLAG_GUIDED_CAP = 4,  /* guided anchors per frame exceed capacity */
     SASSD_FLAG_NMS_CAP = 8,     /* NMS candidates per frame exceed capacity */
-    SASSD_FLAG_HASH_FULL = 16
+    SASSD_FLAG_HASH_FULL = 16,
+    SASSD_FLAG_DET_CAP = 32     /* boxes kept by the NMS exceed the detection capacity */
 };
 
 int sassd_version(void);
@@ -110,8 +111,11 @@ int sassd_anchor_mask(const int32_t* coors, const int32_t* d_rows, int rows_cap,
 int sassd_hash_build(const int32_t* coors, const int32_t* d_rows, int rows_cap, int batch, int D, int H, int W,
                      int32_t* keys, int32_t* vals, int slots, int32_t* d_status, sassd_stream_t stream);
 /* submanifold 3x3x3: output sites == input sites. */
+/* tile_mask (optional): int32 [ceil(rows_cap / 128)], bit k of entry t = some row of rows [128t, 128t+128) has a
+ * neighbour at offset k (consumed by sassd_spconv_f16x3 to skip absent taps). */
 int sassd_rulebook_subm(const int32_t* coors, const int32_t* d_rows, int rows_cap, int D, int H, int W,
-                        const int32_t* keys, const int32_t* vals, int slots, int32_t* nbr, sassd_stream_t stream);
+                        const int32_t* keys, const int32_t* vals, int slots, int32_t* nbr, int32_t* tile_mask,
+                        sassd_stream_t stream);
 /* strided conv (k=3,s=2,p=1): active output set, sorted by flattened (b,z,y,x). */
 size_t sassd_rulebook_conv_workspace_bytes(int batch, int Do, int Ho, int Wo);
 int sassd_rulebook_conv_outputs(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in, int batch,
@@ -120,7 +124,7 @@ int sassd_rulebook_conv_outputs(const int32_t* coors_in, const int32_t* d_rows_i
 /* neighbour table of the strided conv: nbr[o][k] = row of input cell 2*o - 1 + k. */
 int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* d_rows_out, int rows_cap_out, int D, int H, int W,
                             const int32_t* keys_in, const int32_t* vals_in, int slots_in, int32_t* nbr,
-                            sassd_stream_t stream);
+                            int32_t* tile_mask, sassd_stream_t stream);
 int sassd_rulebook_pairs(const int32_t* nbr, const int32_t* d_rows_out, int rows_cap, int32_t* indice_pairs,
                          int32_t* indice_pair_num, sassd_stream_t stream);
 
@@ -186,7 +190,8 @@ int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split,
 #define SASSD_TILE_DIST_MAX 9          /* distances beyond this are stored as any larger value */
 int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack,
                            const float* scale, const float* shift, float* out_f32, void* out_split,
-                           const int32_t* tile_dist, int reach, const float* const_out, sassd_stream_t stream);
+                           const int32_t* tile_dist, int reach, const float* const_out, int32_t* counters,
+                           sassd_stream_t stream);     /* counters: optional int32[2], += tiles computed, += tiles */
 /* dense() of the last sparse tensor straight into a (pre-zeroed) split map [2,batch,H,W,D*C]. */
 int sassd_sparse_to_bev_split(const float* feat, const int32_t* coors, const int32_t* d_rows, int rows_cap, int C,
                               int D, int H, int W, int batch, void* bev_split, int32_t* tile_dist,
@@ -206,8 +211,17 @@ typedef struct {
 size_t sassd_spconv_pack_bytes(int taps, int cin_stored, int cout);
 int sassd_spconv_pack(const float* weight, int taps, int cin, int cin_stored, int cout, void* packed,
                       sassd_stream_t stream);
+/* tile_mask (optional, taps <= 27): int32 per SASSD_SPCONV_TILE_ROWS-row tile of the OUTPUT rows, bit t set when some
+ * row of the tile has a neighbour at tap t (written by sassd_rulebook_subm / sassd_rulebook_conv_nbr); K chunks whose
+ * taps are all absent are skipped (an absent pair contributes exactly zero, so the result is unchanged).
+ * ws (optional, sassd_spconv_workspace_bytes()): scratch for the tap split - when the layer has at most half as many
+ * tiles as CTAs, the two CTAs of a cluster share one tile's chunks and the peer's fp32 partial sums travel through
+ * it.  counters (optional, int32[2], caller-zeroed): += executed (tile, chunk) pairs, += tiles (instrumentation). */
+#define SASSD_SPCONV_TILE_ROWS 128
+size_t sassd_spconv_workspace_bytes(void);
 int sassd_spconv_f16x3(const sassd_spconv_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
-                       const float* shift, const int32_t* nbr, const int32_t* d_rows, void* out_split, float* out_f32,
+                       const float* shift, const int32_t* nbr, const int32_t* tile_mask, const int32_t* d_rows,
+                       void* out_split, float* out_f32, void* ws, size_t ws_bytes, int32_t* counters,
                        sassd_stream_t stream);
 /* fp32 rows [rows, cin] -> split rows [2][rows_cap][cs] (cs >= cin, cs % 8 == 0, padding zero). */
 int sassd_features_to_split(const float* feat, const int32_t* d_rows, int rows_cap, int cin, int cs, void* out_split,
@@ -227,7 +241,9 @@ int sassd_sparse_to_bev(const float* feat, const int32_t* coors, const int32_t* 
 /* ------------------------------------------------------------------------
  * second_box_decode + get_guided_anchors (ssd_rotate_head.py:53-91,307-372):
  * head [batch,H,W,head_stride] NHWC holds conv_box | conv_cls | conv_dir_cls
- * channels back to back; anchors [n_anchors,7] in (class,y,x,rot) order;
+ * channels back to back; anchors [n_anchors,7] in (class,y,x,rot) order, one table shared by the
+ * batch (anchors_per_frame = 0) or one per frame [batch,n_anchors,7] (anchors_per_frame = 1, the
+ * reference's signature: ssd_rotate_head.py:316 indexes anchors[i]);
  * mask [batch,n_anchors] uint8.  Per frame, in anchor order: keep mask &&
  * max_c sigmoid(cls) > thr, decode, flip direction.  Outputs (capacity k_cap per frame):
  * boxes [batch,k_cap,7], labels [batch,k_cap] i32, index [batch,k_cap] i32
@@ -235,7 +251,7 @@ int sassd_sparse_to_bev(const float* feat, const int32_t* coors, const int32_t* 
  * ---------------------------------------------------------------------- */
 size_t sassd_decode_select_workspace_bytes(int batch, int n_anchors);
 int sassd_decode_select(const float* head, int head_stride, int batch, int H, int W, int num_class,
-                        const float* anchors, const uint8_t* mask, int n_anchors, float thr,
+                        const float* anchors, int anchors_per_frame, const uint8_t* mask, int n_anchors, float thr,
                         float* boxes, int32_t* labels, int32_t* index, int32_t* d_k, int k_cap,
                         int32_t* d_status, void* ws, size_t ws_bytes, sassd_stream_t stream);
 

@@ -40,7 +40,7 @@ _CALIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth_calib.n
 
 
 def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, num_parts=28,
-                              cls_gain=2.0, cls_bias=-5.0, calibrated=True):
+                              cls_gain=20.0, cls_bias=-7.5, ps_gain=8.0, ps_offset=1.4, calibrated=True):
     """Random-but-fixed weights in the reference's state_dict naming.
 
     No checkpoint is reachable offline, so benchmarks and parity tests use these.
@@ -72,14 +72,15 @@ def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, 
     s = math.sqrt(1.0 / num_filters)
     sd[p + "conv_cls.weight"] = torch.randn(na * num_class, num_filters, 1, 1, generator=g) * s * cls_gain
     sd[p + "conv_cls.bias"] = torch.randn(na * num_class, generator=g) * 0.05 + cls_bias
-    sd[p + "conv_box.weight"] = torch.randn(na * 7, num_filters, 1, 1, generator=g) * s * 0.15
+    sd[p + "conv_box.weight"] = torch.randn(na * 7, num_filters, 1, 1, generator=g) * s * 1.5
     sd[p + "conv_box.bias"] = torch.randn(na * 7, generator=g) * 0.02
     sd[p + "conv_dir_cls.weight"] = torch.randn(na * 2, num_filters, 1, 1, generator=g) * s
     sd[p + "conv_dir_cls.bias"] = torch.randn(na * 2, generator=g) * 0.05
     p = "extra_head."
     sd[p + "convs.0.weight"] = torch.randn(num_parts, num_filters, 3, 3, generator=g) * math.sqrt(2.0 / (num_filters * 9))
     _bn(sd, p + "convs.1", num_parts, g)
-    sd[p + "convs.3.weight"] = torch.randn(num_parts, num_parts, 1, 1, generator=g) * math.sqrt(2.0 / num_parts)
+    sd[p + "convs.3.weight"] = (torch.randn(num_parts, num_parts, 1, 1, generator=g) * ps_gain - ps_offset) * \
+        math.sqrt(2.0 / num_parts)
     if calibrated and seed == 0 and num_filters == 256 and bev_in == 320 and os.path.isfile(_CALIB):
         # BatchNorm running statistics as training-mode BN would have recorded them on synthetic
         # frames (tests/tools/calibrate_synthetic_weights.py): keeps activations O(1) in all 22 layers
@@ -97,13 +98,15 @@ def save_checkpoint(state_dict, filename, epoch=0, it=0, module_prefix=False):
                 "version": "sassd_b200"}, filename)
 
 
-def load_params_from_file(model, filename, to_cpu=False, verbose=False):
+def load_params_from_file(model, filename, to_cpu=False, verbose=False, allow_pickle=False):
     """Mirror of tools/train_utils/__init__.py:154-180: copy every key whose name
     (after stripping an optional ``module.`` prefix) and shape match; report the
-    rest.  Returns (n_loaded, missing_keys)."""
+    rest.  Returns (n_loaded, missing_keys).  The reference format holds tensors and plain scalars only, so the
+    file is read with ``weights_only=True``; ``allow_pickle=True`` opts into arbitrary pickles for legacy files
+    from a trusted source."""
     if not os.path.isfile(filename):
         raise FileNotFoundError(filename)
-    ckpt = torch.load(filename, map_location="cpu" if to_cpu else None, weights_only=False)
+    ckpt = torch.load(filename, map_location="cpu" if to_cpu else None, weights_only=not allow_pickle)
     disk = ckpt["model_state"] if isinstance(ckpt, dict) and "model_state" in ckpt else ckpt
     return load_state_dict_into(model, disk, verbose=verbose)
 

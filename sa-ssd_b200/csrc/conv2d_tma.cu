@@ -76,6 +76,7 @@ struct Conv2dArgs {
     const int* tile_dist; // optional: distance of each tile to the nearest active cell of the scattered map
     const float* cvec;    // output constant of the tiles that see a constant input (tile_dist > reach, not on the border)
     int reach;
+    int* counters;        // optional [2]: += tiles computed (not stored as a constant), += tiles (bench instrumentation)
     int tile_order;       // 1: computed tiles first (SASSD_TMA_ORDER=1), 0: round-robin
     int dbg;              // SASSD_TMA_DBG (timing experiments only): 1 = reuse stale B stages, 2 = reuse stale A stages,
                           // 4 = plain MMAs (no operand collector)
@@ -214,7 +215,8 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + C::OUT_STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
     pdl_launch_dependents();      // the next layer may be scheduled as this grid's CTAs retire
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so that the compiler knows it is warp-uniform (role loops on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.H + TILE_H - 1) / TILE_H;
     const int ntiles = p.batch * tiles_y * tiles_x;
     const int kchunks = (p.cin + BKC - 1) / BKC;
@@ -301,53 +303,64 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             }
         }
     } else if (warp == WARP_ISSUE) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, 0u /*F16*/);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
-                const int tile = tile_at(k);
-                if (tile_is_constant(p, tile, (tile / tiles_x) % tiles_y, tile % tiles_x, tiles_y, tiles_x)) continue;
-                mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
+        // Warp-convergent loop (uniform datapath), one elected lane issues.  Round 2: this loop, not the tensor pipe,
+        // was the bound - rebuilding four 64-bit descriptors per K=16 step plus a run-time debug variant cost ~60 SASS
+        // instructions per three MMAs (profiles/r2_mma_issue_probe.md) - so a descriptor is now a per-stage low word
+        // plus immediates and the three products are straight-line code.
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0u /*F16*/);
+        constexpr uint32_t kStageLo = (uint32_t)C::STAGE_BYTES >> 4, kATileLo = (uint32_t)A_TILE_BYTES >> 4,
+                           kBTileLo = (uint32_t)C::B_TILE_BYTES >> 4;
+        const bool leader = elect_one();
+        const uint32_t lo0 = desc_lo(base);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int computed = 0;
+        for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
+            const int tile = tile_at(k);
+            if (tile_is_constant(p, tile, (tile / tiles_x) % tiles_y, tile % tiles_x, tiles_y, tiles_x)) continue;
+            ++computed;
+            mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
+            uint32_t first = 0u;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                mbar_wait(full(stage), phase);
                 tc_fence_after();
-                const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    mbar_wait(full(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
+                const uint32_t ah = lo0 + (uint32_t)stage * kStageLo, al = ah + kATileLo;
+                const uint32_t bh = al + kATileLo, bl = bh + kBTileLo;
+                if (leader) {
+                    // Each K=16 step reads one operand once for two of its three products: bh through the
+                    // weight-stationary form's B collector when N = 256 (B is the larger operand), ah through the A
+                    // collector otherwise.
 #pragma unroll
-                    for (int k16 = 0; k16 < 4; ++k16) {
-                        const uint32_t ko = (uint32_t)k16 * 32u;
-                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        const uint32_t first = (ch | k16) ? 1u : 0u;
-                        // An SS-mode MMA is paced by its shared-memory operand reads (~64 B/clk: 192 clk for
-                        // 128x256x16 against a 128-clk tensor floor), so each K=16 step reads one operand once for
-                        // two of its three products: bh through the weight-stationary form's B collector when
-                        // N = 256 (B is the larger operand), ah through the A collector otherwise.
-                        if (p.dbg & 4) {
-                            mma_f16(d_small, dal, dbh, idesc, first);
-                            mma_f16(d_big, dah, dbh, idesc, first);
-                            mma_f16(d_small, dah, dbl, idesc, 1u);
-                        } else if constexpr (BN == 256) {
-                            mma_f16_ws<1>(d_big, dah, dbh, idesc, first);
-                            mma_f16_ws<2>(d_small, dal, dbh, idesc, first);
-                            mma_f16_ws<0>(d_small, dah, dbl, idesc, 1u);
+                    for (uint32_t k16 = 0; k16 < 4; ++k16) {
+                        const uint32_t ko = k16 * kDescK16;
+                        const uint32_t f = k16 ? 1u : first;
+                        if constexpr (BN == 256) {
+                            mma_f16_ws_lo<1>(d_big, ah + ko, bh + ko, idesc, f);
+                            mma_f16_ws_lo<2>(d_small, al + ko, bh + ko, idesc, f);
+                            mma_f16_ws_lo<0>(d_small, ah + ko, bl + ko, idesc, 1u);
                         } else {
-                            mma_f16(d_small, dal, dbh, idesc, first);
-                            mma_f16_akeep(d_big, dah, dbh, idesc, first);
-                            mma_f16_areuse(d_small, dah, dbl, idesc, 1u);
+                            mma_f16_lo(d_small, al + ko, bh + ko, idesc, f);
+                            mma_f16_acoll_lo<1>(d_big, ah + ko, bh + ko, idesc, f);
+                            mma_f16_acoll_lo<2>(d_small, ah + ko, bl + ko, idesc, 1u);
                         }
                     }
                     mma_commit(empty(stage));
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit(tmem_full(acc));
-                if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
+                __syncwarp();
+                first = 1u;
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
+            if (leader) mma_commit(tmem_full(acc));
+            __syncwarp();
+            if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (p.counters && leader) {
+            if (computed) atomicAdd(&p.counters[0], computed);
+            if (blockIdx.x == 0) atomicAdd(&p.counters[1], ntiles);
         }
     } else if (warp < EPI_WARPS) {
         int acc = 0;
@@ -440,6 +453,18 @@ __device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t da, uint6
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void mma_f16_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -462,7 +487,7 @@ conv2d_tma_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_co
     const uint32_t tmem_slot = tmem_full + 16u;
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + (tmem_slot - base));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -522,32 +547,40 @@ conv2d_tma_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_co
             }
         }
     } else if (warp == WARP_ISSUE) {
-        if (lane == 0 && leader) {
+        if (leader) {       // leader CTA: warp-convergent loop, one elected lane issues for the pair (see conv2d_tma_kernel)
             constexpr uint32_t idesc = make_idesc(2 * BM, BN, 0u /*F16*/);
+            constexpr uint32_t kStageLo = (uint32_t)STAGE_2CTA_BYTES >> 4, kATileLo = (uint32_t)A_TILE_BYTES >> 4,
+                               kBHalfLo = (uint32_t)B_HALF_BYTES >> 4;
+            const bool issuer = elect_one();
+            const uint32_t lo0 = desc_lo(base);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t d_big = tmem_base, d_small = tmem_base + (uint32_t)BN;
             for (int pair = cluster_id; pair < npairs; pair += nclusters) {
                 mbar_wait_cluster(tmem_empty, acc_phase ^ 1u);
                 tc_fence_after();
+                uint32_t first = 0u;
                 for (int ch = 0; ch < nchunks; ++ch) {
                     mbar_wait(full(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_hi = base + stage * STAGE_2CTA_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_HALF_BYTES;
+                    const uint32_t ah = lo0 + (uint32_t)stage * kStageLo, al = ah + kATileLo;
+                    const uint32_t bh = al + kATileLo, bl = bh + kBHalfLo;
+                    if (issuer) {
 #pragma unroll
-                    for (int k16 = 0; k16 < 4; ++k16) {
-                        const uint32_t ko = (uint32_t)k16 * 32u;
-                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-                        const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-                        mma_f16_pair(d_small, dal, dbh, idesc, (ch | k16) ? 1u : 0u);
-                        mma_f16_pair(d_small, dah, dbl, idesc, 1u);
-                        mma_f16_pair(d_big, dah, dbh, idesc, (ch | k16) ? 1u : 0u);
+                        for (uint32_t k16 = 0; k16 < 4; ++k16) {
+                            const uint32_t ko = k16 * kDescK16, f = k16 ? 1u : first;
+                            mma_f16_pair_lo(d_small, al + ko, bh + ko, idesc, f);
+                            mma_f16_pair_lo(d_small, ah + ko, bl + ko, idesc, 1u);
+                            mma_f16_pair_lo(d_big, ah + ko, bh + ko, idesc, f);
+                        }
+                        mma_commit_pair(empty(stage));
                     }
-                    mma_commit_pair(empty(stage));
+                    __syncwarp();
+                    first = 1u;
                     if (++stage == STAGES_2CTA) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit_pair(tmem_full);
+                if (issuer) mma_commit_pair(tmem_full);
+                __syncwarp();
                 acc_phase ^= 1u;
             }
         }
@@ -621,14 +654,24 @@ static int launch2(const CUtensorMap& map, const CUtensorMap& omap, const Conv2d
 extern "C" int sassd_conv2d_f16x3(const sassd_conv2d_desc* d, const void* in_split, const void* wpack,
                                   const float* scale, const float* shift, float* out_f32, void* out_split,
                                   sassd_stream_t stream_) {
-    return sassd_conv2d_f16x3_occ(d, in_split, wpack, scale, shift, out_f32, out_split, nullptr, 0, nullptr, stream_);
+    return sassd_conv2d_f16x3_occ(d, in_split, wpack, scale, shift, out_f32, out_split, nullptr, 0, nullptr, nullptr, stream_);
 }
 
 extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in_split, const void* wpack,
                                       const float* scale, const float* shift, float* out_f32, void* out_split,
-                                      const int32_t* tile_dist, int reach, const float* const_out,
+                                      const int32_t* tile_dist, int reach, const float* const_out, int32_t* counters,
                                       sassd_stream_t stream_) {
     if (tile_dist && (!const_out || reach < 0)) return SASSD_ERR_ARG;
+    if (tile_dist) {
+        // The constant-region rule is exact only while (a) the layer is within the range tile distances are recorded
+        // for and (b) the zero-padding disturbance (reach-1 pixels deep) stays inside the outermost tile row / column,
+        // the only tiles the kernel exempts - a thin partial edge tile would let it spill into a skipped tile.
+        const int last_h = d ? d->H - (d->H - 1) / SASSD_CONV2D_TILE_H * SASSD_CONV2D_TILE_H : 0;
+        const int last_w = d ? d->W - (d->W - 1) / SASSD_CONV2D_TILE_W * SASSD_CONV2D_TILE_W : 0;
+        const int edge = last_h < last_w ? last_h : last_w;
+        if (reach > SASSD_TILE_DIST_MAX || (edge < SASSD_CONV2D_TILE_H ? edge : SASSD_CONV2D_TILE_H) < reach - 1)
+            return SASSD_ERR_UNSUPPORTED;
+    }
     using namespace tma;
     if (!d || !in_split || !wpack || (!out_f32 && !out_split)) return SASSD_ERR_ARG;
     if (d->batch < 1 || d->H < 1 || d->W < 1 || d->cin < 1 || d->cout < 1 || d->cout > 256) return SASSD_ERR_ARG;
@@ -652,7 +695,7 @@ extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in
     a.wpack = wpack; a.scale = scale; a.shift = shift; a.out_f32 = out_f32; a.out_split = (__half*)out_split;
     a.batch = d->batch; a.H = d->H; a.W = d->W; a.cin = d->cin; a.cout = d->cout; a.taps = d->taps; a.relu = d->relu;
     a.out_f32_stride = d->out_f32_stride; a.out_split_ch = d->out_split_ch;
-    a.tile_dist = tile_dist; a.reach = reach; a.cvec = const_out;
+    a.tile_dist = tile_dist; a.reach = reach; a.cvec = const_out; a.counters = counters;
     static const int tile_order = [] { const char* e = getenv("SASSD_TMA_ORDER"); return e ? atoi(e) : 0; }();
     a.tile_order = tile_order;
     static const int dbg = [] { const char* e = getenv("SASSD_TMA_DBG"); return e ? atoi(e) : 0; }();

@@ -69,7 +69,7 @@ ds_count_kernel(const float* __restrict__ head, HeadLayout L, const uint8_t* __r
 
 __global__ void __launch_bounds__(256)
 ds_emit_kernel(const float* __restrict__ head, HeadLayout L, const float* __restrict__ anchors,
-               const uint8_t* __restrict__ mask, float thr, int nchunks, const int* __restrict__ chunk_count,
+               size_t anchor_frame_stride, const uint8_t* __restrict__ mask, float thr, int nchunks, const int* __restrict__ chunk_count,
                float* __restrict__ boxes, int* __restrict__ labels, int* __restrict__ index, int* __restrict__ d_k,
                int k_cap, int* __restrict__ status) {
     __shared__ int s_scan[33];
@@ -110,7 +110,7 @@ ds_emit_kernel(const float* __restrict__ head, HeadLayout L, const float* __rest
             anchor_decompose(L, a, cls_a, pix, rot);
             const float* px = head_b + (size_t)pix * L.stride;
             const float* e = px + cls_a * 14 + rot * 7;               // xt yt zt wt lt ht rt
-            const float* an = anchors + (size_t)a * 7;                // xa ya za wa la ha ra
+            const float* an = anchors + (size_t)b * anchor_frame_stride + (size_t)a * 7;   // xa ya za wa la ha ra
             const float xa = __ldg(an + 0), ya = __ldg(an + 1), za = __ldg(an + 2), wa = __ldg(an + 3),
                         la = __ldg(an + 4), ha = __ldg(an + 5), ra = __ldg(an + 6);
             // second_box_decode, op by op in fp32 without contraction (torch evaluates each op separately)
@@ -142,7 +142,8 @@ extern "C" size_t sassd_decode_select_workspace_bytes(int batch, int n_anchors) 
 }
 
 extern "C" int sassd_decode_select(const float* head, int head_stride, int batch, int H, int W, int num_class,
-                                   const float* anchors, const uint8_t* mask, int n_anchors, float thr, float* boxes,
+                                   const float* anchors, int anchors_per_frame, const uint8_t* mask, int n_anchors,
+                                   float thr, float* boxes,
                                    int32_t* labels, int32_t* index, int32_t* d_k, int k_cap, int32_t* d_status,
                                    void* ws, size_t ws_bytes, sassd_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -157,7 +158,7 @@ extern "C" int sassd_decode_select(const float* head, int head_stride, int batch
     const int nchunks = (n_anchors + DS_CHUNK - 1) / DS_CHUNK;
     dim3 grid(nchunks, batch);
     ds_count_kernel<<<grid, 256, 0, stream>>>(head, L, mask, thr, nchunks, (int*)ws);
-    ds_emit_kernel<<<grid, 256, 0, stream>>>(head, L, anchors, mask, thr, nchunks, (const int*)ws, boxes, labels, index,
+    ds_emit_kernel<<<grid, 256, 0, stream>>>(head, L, anchors, anchors_per_frame ? (size_t)n_anchors * 7 : 0, mask, thr, nchunks, (const int*)ws, boxes, labels, index,
                                              d_k, k_cap, d_status);
     return sassd_check_launch();
 }

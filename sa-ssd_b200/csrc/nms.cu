@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256)
 nms_gather_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ d_n,
                   const float* __restrict__ boxes7, const int* __restrict__ labels, int k_cap,
                   const float* __restrict__ s_sorted, const int* __restrict__ src_sorted, float* __restrict__ det,
-                  int* __restrict__ d_ndet, int det_cap) {
+                  int* __restrict__ d_ndet, int det_cap, int* __restrict__ status) {
     constexpr int COLB = CAP / 64;
     __shared__ unsigned long long s_remv[COLB], s_keep[COLB], s_diag[64], s_keepw;
     __shared__ int s_pref[COLB + 1];
@@ -317,6 +317,9 @@ nms_gather_kernel(const unsigned long long* __restrict__ mask, const int* __rest
         for (int c = 0; c < colb; ++c) { s_pref[c] = acc; acc += __popcll(s_keep[c]); }
         s_pref[colb] = acc;
         d_ndet[f] = acc < det_cap ? acc : det_cap;
+        // the reference applies no per-image maximum (get_rescore_bboxes ignores max_per_img): dropping kept boxes
+        // must not pass silently
+        if (acc > det_cap) atomicOr(status, SASSD_FLAG_DET_CAP);
     }
     __syncthreads();
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
@@ -401,7 +404,7 @@ extern "C" int sassd_rescore_nms(const float* boxes, const float* scores, const 
     dim3 grid(128, batch);
     nms_mask_kernel<<<grid, NMS_MASK_THREADS, 0, stream>>>(boxes5, d_n, 0, kNmsCap, COLB, iou_thr, mask);
     nms_gather_kernel<kNmsCap><<<batch, 256, 0, stream>>>(mask, d_n, boxes, labels, k_cap, s_sorted, src_sorted, det,
-                                                          d_ndet, det_cap);
+                                                          d_ndet, det_cap, d_status);
     return sassd_check_launch();
 }
 

@@ -14,7 +14,9 @@
 //                   flattened index (the canonical order) — no sort, no
 //                   thrust::unique, no dense int32 grid as in spconv v1.
 //  * nbr fill     : one thread per (output row, offset) probes the input hash;
-//                   writes are fully coalesced.
+//                   a CTA stages one 128-row tile of the table in shared memory,
+//                   writes it with one bulk (TMA) store and records which of the
+//                   27 offsets occur in the tile (tile mask for tap skipping).
 #include "common.cuh"
 
 __device__ __forceinline__ int flat_key(int b, int z, int y, int x, int D, int H, int W) {
@@ -54,46 +56,91 @@ extern "C" int sassd_hash_build(const int32_t* coors, const int32_t* d_rows, int
     return sassd_check_launch();
 }
 
-// nbr[o*27 + k] = row of input cell  stride*o - pad + k  (stride=1,pad=1: SubM; stride=2,pad=1: strided)
+// nbr[o*27 + k] = row of input cell  stride*o - pad + k  (stride=1,pad=1: SubM; stride=2,pad=1: strided).
+// One CTA builds the table rows of one 128-row tile (SASSD_SPCONV_TILE_ROWS) in shared memory - one thread per
+// (row, offset) probe of the input hash - and writes them with ONE bulk (TMA) store: the tile's rows are a contiguous
+// 13.8 KB block of the table, so the write is fully coalesced and off the LSU.  While the entries are in flight the
+// warps OR together which of the 27 offsets occur in the tile at all (ballot per offset is overkill: a warp-wide
+// __reduce_or of the per-lane bit, then one shared atomicOr per warp); that 27-bit tile mask is what lets the sparse
+// conv skip absent taps.
+#define NBR_TILE_ROWS SASSD_SPCONV_TILE_ROWS
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+#define NBR_THREADS 1024      // 3456 probes per tile: <= 4 independent (latency-bound) hash probes in flight per thread
 template <int STRIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NBR_THREADS)
 nbr_fill_kernel(const int4* __restrict__ coors_out, const int* __restrict__ d_rows, int rows_cap, int D, int H, int W,
-                const int* __restrict__ keys, const int* __restrict__ vals, int slots, int* __restrict__ nbr) {
+                const int* __restrict__ keys, const int* __restrict__ vals, int slots, int* __restrict__ nbr,
+                int* __restrict__ tile_mask) {
+    __shared__ __align__(128) int s_tile[NBR_TILE_ROWS * 27];
+    __shared__ unsigned int s_mask;
     const int rows = min(*d_rows, rows_cap);
-    const long long total = (long long)rows * 27;
+    const int ntiles = (rows + NBR_TILE_ROWS - 1) / NBR_TILE_ROWS;
     const uint32_t mask = (uint32_t)slots - 1u;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int o = (int)(t / 27), k = (int)(t - (long long)o * 27);
-        const int4 c = __ldg(&coors_out[o]);
-        const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
-        const int z = c.y * STRIDE - 1 + kz, y = c.z * STRIDE - 1 + ky, x = c.w * STRIDE - 1 + kx;
-        int res = -1;
-        if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
-            const int slot = sassd_hash_find(keys, mask, flat_key(c.x, z, y, x, D, H, W));
-            if (slot >= 0) res = __ldg(&vals[slot]);
+    const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(s_tile);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) s_mask = 0u;
+        __syncthreads();
+        const int row0 = tile * NBR_TILE_ROWS;
+        const int rows_here = min(NBR_TILE_ROWS, rows_cap - row0);       // table rows this tile owns (capacity)
+        unsigned int my_bits = 0u;
+#pragma unroll 4
+        for (int t = threadIdx.x; t < rows_here * 27; t += NBR_THREADS) {
+            const int o = t / 27, k = t - o * 27;
+            int res = -1;
+            if (row0 + o < rows) {
+                const int4 c = __ldg(&coors_out[row0 + o]);
+                const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
+                const int z = c.y * STRIDE - 1 + kz, y = c.z * STRIDE - 1 + ky, x = c.w * STRIDE - 1 + kx;
+                if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
+                    const int slot = sassd_hash_find(keys, mask, flat_key(c.x, z, y, x, D, H, W));
+                    if (slot >= 0) res = __ldg(&vals[slot]);
+                }
+            }
+            s_tile[t] = res;
+            if (res >= 0) my_bits |= 1u << k;
         }
-        nbr[t] = res;
+        my_bits = __reduce_or_sync(0xffffffffu, my_bits);
+        if ((threadIdx.x & 31) == 0 && my_bits) atomicOr(&s_mask, my_bits);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the bulk copy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(rows_here * 27 * 4);
+            const uint32_t bulk = bytes & ~15u;
+            int* dst = nbr + (size_t)row0 * 27;
+            if (bulk) bulk_s2g(dst, s_addr, bulk);
+            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) dst[i] = s_tile[i];       // < 16-byte tail of a ragged table
+            if (tile_mask) tile_mask[tile] = (int)s_mask;
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");            // s_tile may be overwritten
+        }
+        __syncthreads();
     }
+}
+
+static int nbr_grid(int rows_cap) {
+    const int tiles = sassd_div_up(rows_cap, NBR_TILE_ROWS);
+    return tiles < 148 * 2 ? (tiles > 0 ? tiles : 1) : 148 * 2;
 }
 
 extern "C" int sassd_rulebook_subm(const int32_t* coors, const int32_t* d_rows, int rows_cap, int D, int H, int W,
                                    const int32_t* keys, const int32_t* vals, int slots, int32_t* nbr,
-                                   sassd_stream_t stream_) {
+                                   int32_t* tile_mask, sassd_stream_t stream_) {
     if (!coors || !d_rows || !keys || !vals || !nbr) return SASSD_ERR_ARG;
     if (rows_cap <= 0) return SASSD_OK;
-    nbr_fill_kernel<1><<<sassd_grid((long long)rows_cap * 27, 256), 256, 0, (cudaStream_t)stream_>>>(
-        (const int4*)coors, d_rows, rows_cap, D, H, W, keys, vals, slots, nbr);
+    nbr_fill_kernel<1><<<nbr_grid(rows_cap), NBR_THREADS, 0, (cudaStream_t)stream_>>>(
+        (const int4*)coors, d_rows, rows_cap, D, H, W, keys, vals, slots, nbr, tile_mask);
     return sassd_check_launch();
 }
 
 extern "C" int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* d_rows_out, int rows_cap_out, int D,
                                        int H, int W, const int32_t* keys_in, const int32_t* vals_in, int slots_in,
-                                       int32_t* nbr, sassd_stream_t stream_) {
+                                       int32_t* nbr, int32_t* tile_mask, sassd_stream_t stream_) {
     if (!coors_out || !d_rows_out || !keys_in || !vals_in || !nbr) return SASSD_ERR_ARG;
     if (rows_cap_out <= 0) return SASSD_OK;
-    nbr_fill_kernel<2><<<sassd_grid((long long)rows_cap_out * 27, 256), 256, 0, (cudaStream_t)stream_>>>(
-        (const int4*)coors_out, d_rows_out, rows_cap_out, D, H, W, keys_in, vals_in, slots_in, nbr);
+    nbr_fill_kernel<2><<<nbr_grid(rows_cap_out), NBR_THREADS, 0, (cudaStream_t)stream_>>>(
+        (const int4*)coors_out, d_rows_out, rows_cap_out, D, H, W, keys_in, vals_in, slots_in, nbr, tile_mask);
     return sassd_check_launch();
 }
 
@@ -102,35 +149,48 @@ extern "C" int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* 
 // ---------------------------------------------------------------------------
 #define BM_CHUNK 1024  // bitmap words per scan chunk
 
-__global__ void conv_mark_kernel(const int4* __restrict__ coors_in, const int* __restrict__ d_rows, int rows_cap,
-                                 int Do, int Ho, int Wo, uint32_t* __restrict__ bitmap) {
+// Warp-aggregated marking: a warp covers 4 input rows x 8 candidate outputs; neighbouring inputs feed the same
+// output cells, so lanes that hit the same bitmap word find each other (__match_any_sync), OR their bits in the warp
+// and one lane issues the atomicOr.
+__global__ void __launch_bounds__(256)
+conv_mark_kernel(const int4* __restrict__ coors_in, const int* __restrict__ d_rows, int rows_cap,
+                 int Do, int Ho, int Wo, uint32_t* __restrict__ bitmap) {
     const int rows = min(*d_rows, rows_cap);
     const long long total = (long long)rows * 8;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(t >> 3), v = (int)(t & 7);
-        const int4 c = __ldg(&coors_in[r]);
-        // i = 2*o - 1 + k, k in {0,1,2}: odd i -> o in {(i+1)/2 (k=0), (i-1)/2 (k=2)}; even i -> o = i/2 (k=1)
-        int oz, oy, ox;
-        bool ok = true;
-        {
-            const int i = c.y, sel = (v >> 2) & 1;
-            if (i & 1) oz = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { oz = i >> 1; ok &= (sel == 0); }
-            ok &= (oz >= 0 && oz < Do);
-        }
-        {
-            const int i = c.z, sel = (v >> 1) & 1;
-            if (i & 1) oy = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { oy = i >> 1; ok &= (sel == 0); }
-            ok &= (oy >= 0 && oy < Ho);
-        }
-        {
-            const int i = c.w, sel = v & 1;
-            if (i & 1) ox = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { ox = i >> 1; ok &= (sel == 0); }
-            ok &= (ox >= 0 && ox < Wo);
-        }
+    const int lane = threadIdx.x & 31;
+    for (long long t0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); t0 < total;
+         t0 += (long long)gridDim.x * blockDim.x) {
+        const long long t = t0 + lane;
+        bool ok = t < total;
+        int cell = 0;
         if (ok) {
-            const int cell = flat_key(c.x, oz, oy, ox, Do, Ho, Wo);
-            atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+            const int r = (int)(t >> 3), v = (int)(t & 7);
+            const int4 c = __ldg(&coors_in[r]);
+            // i = 2*o - 1 + k, k in {0,1,2}: odd i -> o in {(i+1)/2 (k=0), (i-1)/2 (k=2)}; even i -> o = i/2 (k=1)
+            int oz, oy, ox;
+            {
+                const int i = c.y, sel = (v >> 2) & 1;
+                if (i & 1) oz = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { oz = i >> 1; ok &= (sel == 0); }
+                ok &= (oz >= 0 && oz < Do);
+            }
+            {
+                const int i = c.z, sel = (v >> 1) & 1;
+                if (i & 1) oy = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { oy = i >> 1; ok &= (sel == 0); }
+                ok &= (oy >= 0 && oy < Ho);
+            }
+            {
+                const int i = c.w, sel = v & 1;
+                if (i & 1) ox = sel ? (i - 1) >> 1 : (i + 1) >> 1; else { ox = i >> 1; ok &= (sel == 0); }
+                ok &= (ox >= 0 && ox < Wo);
+            }
+            if (ok) cell = flat_key(c.x, oz, oy, ox, Do, Ho, Wo);
+        }
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int word = cell >> 5;
+            const unsigned peers = __match_any_sync(okmask, word);
+            const uint32_t bits = __reduce_or_sync(peers, 1u << (cell & 31));
+            if (lane == __ffs(peers) - 1) atomicOr(&bitmap[word], bits);
         }
     }
 }

@@ -2,15 +2,23 @@
 // mmdet/models/necks/cmn.py:145-173,192-231) on tcgen05 FP16x3 with the features kept in "split rows":
 // two fp16 planes [2][rows_cap][C] (hi = half(x), lo = half((x - hi) * 2048)), C a multiple of 8.
 //
-// Why: ncu on gconv_tc.cu's TABLE mode (fp32 rows gathered through registers, split on the fly) shows the
-// producers — not the tensor pipe (28 %), not L2 (14 %) — as the limit.  Here a producer thread only *issues* eight
-// 16-byte cp.async copies per chunk (zero fill for missing neighbours) straight into the 128B-swizzled operand tiles
-// and one asynchronous mbarrier arrive that fires when they have landed; no thread waits for data, no registers
-// are staged and no split math runs in the main loop (the producing layer's epilogue wrote the planes).  The per-chunk
-// timeline of a CTA (SASSD_SPS_DBG=64, profiles/r1_timeline_spconv_split.md) then shows the MMA-issuing lane as the
-// critical path, so everything else is taken off it: a helper warp does the generic->async proxy fence, the tile's
-// neighbour indices arrive by one bulk copy, two MMAs per K=16 step instead of three (N-concatenated weights), and
-// the narrow layers pack several taps into one 64-wide K chunk.
+// Structure (one CTA = one 128-row output tile at a time, output-stationary, no atomics, deterministic):
+//   * 8 producer warps only *issue* 16-byte cp.async gathers (zero fill for missing neighbours) straight into the
+//     128B-swizzled operand tiles plus an asynchronous mbarrier arrive; nobody waits for data.  The tile's [128,27]
+//     neighbour indices arrive by one bulk copy.
+//   * a helper warp does the generic->async proxy fence, one lane streams the weight blocks with cp.async.bulk.
+//   * the MMA warp runs its loop warp-convergent (uniform datapath), one elected lane issues
+//     x*w = ah*bh + (ah*bl + al*bh)/2048 as TWO instructions per K=16 step: ah x [bh | bl] (N = 2*BN) and al x bh.
+//     Round 2: the issue loop itself was the bound (profiles/r2_mma_issue_probe.md: ~20 SASS instructions per UTCHMMA
+//     = 100-130 clk against a 32-64 clk tensor floor), so descriptors are a per-stage low word + immediates.
+//   * narrow layers pack 2/4/8 taps into one 64-wide K chunk.
+//   * tap skipping (round 2): the rulebook kernel records, per 128-row tile, which of the 27 taps have a neighbour
+//     at all (tile_mask); chunks whose taps are all absent are skipped by every role - reference semantics only need
+//     the listed pairs (spconv's indice_pairs), an absent pair contributes exactly zero.
+//   * small layers (2 * tiles <= CTAs, i.e. one frame at a time): the two CTAs of a cluster split the active chunks
+//     of ONE tile (split-K over taps); the peer hands its fp32 partial sums to the leader through an L2-resident
+//     scratch row block and a remote mbarrier arrive (release/acquire at cluster scope), the leader adds them in a
+//     fixed order and runs the epilogue.  A 45-tile layer then occupies 90 SMs with half the chunk chain each.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -25,7 +33,8 @@ constexpr int BKC = 64;                 // channels per chunk
 constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
 constexpr int THREADS3 = (EPI_WARPS + PROD_WARPS + 3) * 32;   // 480
 constexpr int W_MMA = EPI_WARPS + PROD_WARPS, W_BLOAD = W_MMA + 1, W_FENCE = W_MMA + 2;
-constexpr int TRACE_CHUNKS = 81;
+constexpr int CLUSTER = 2;              // CTAs per cluster (tap split for small layers)
+constexpr int SPLIT_TILES_MAX = 74;     // tiles of the scratch block (148 SMs / CLUSTER)
 
 template <int BN>
 struct Cfg3 {
@@ -46,6 +55,26 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {   // arrive when this thread's prior cp.async land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {    // acquire at cluster scope
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAITC_DONE;\n\t"
+        "bra.uni WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 
 struct Args {
     const __half* in;       // [2][in_rows_cap][cin]
@@ -54,18 +83,46 @@ struct Args {
     const float* scale;
     const float* shift;
     const int* nbr;
+    const int* tile_mask;   // [tiles] bit t = some row of the tile has a neighbour at tap t (null: all taps)
     const int* d_rows;
     __half* out_split;      // [2][rows_cap][out_ch] or null
     size_t out_plane;
     float* out_f32;         // [rows_cap][out_f32_stride] or null
+    float* scratch;         // [SPLIT_TILES_MAX][128][BN] fp32 partial sums of the peer CTA (null: no tap split)
+    int* counters;          // optional [2]: executed (tile, chunk) pairs, tiles (bench instrumentation)
+    long long* trace;       // optional [grid][16] clock64 sums per CTA (SASSD_SPS_TRACE=1, timing experiments only)
     int cin, cout, taps, rows_cap, relu, out_ch, out_f32_stride;
-    long long* trace;       // dbg & 64: per-chunk clock64() stamps of CTA 0 [3 agents][TRACE_CHUNKS][4]
-    int dbg;                // SASSD_SPS_DBG (timing experiments only): 8 = stale weight stages, 16 = no MMAs,
-                            // 32 = no gather copies, 64 = dump CTA 0's timeline, 128 = MMA lane fences itself
+    int dbg;                // SASSD_SPS_DBG (timing experiments only): 1 = no tap skipping, 2 = no tap split,
+                            // 16 = no MMAs, 32 = no gather copies
 };
 
-template <int TABLE, int BN>
-__global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p) {
+// The chunks of one tile this CTA executes, identical in every role: chunk g is active when one of its taps is in the
+// tile's mask; with a tap split the active chunks are dealt out alternately to the two CTAs of the cluster.
+struct ChunkSet {
+    uint32_t mask;     // bit g = chunk g is executed by this CTA
+    __device__ __forceinline__ ChunkSet(uint32_t tap_mask, int tpg, int nchunks, int part, int nparts) {
+        uint32_t act = tap_mask;
+        if (tpg > 1) {
+            const uint32_t group = (1u << tpg) - 1u;
+            act = 0u;
+            for (int g = 0; g < nchunks; ++g)
+                if ((tap_mask >> (g * tpg)) & group) act |= 1u << g;
+        }
+        if (nparts == 1) { mask = act; return; }
+        uint32_t m = 0u, rest = act;          // deal the active chunks out alternately (nparts == 2)
+        for (int j = 0; rest; ++j) {
+            const uint32_t low = rest & (0u - rest);
+            if ((j & 1) == part) m |= low;
+            rest ^= low;
+        }
+        mask = m;
+    }
+};
+
+// CS = stored input channels per tap (8 / 16 / 32 / 64) as a compile-time constant for the layers of the network - the
+// producers' piece / tap arithmetic then folds to shifts - or 0 for any other width (run-time arithmetic).
+template <int TABLE, int BN, int CS>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p) {
     using C = Cfg3<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,19 +138,24 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     auto tmem_empty = [&](int a) { return bar_base + 8u * (4 * C::STAGES + 2 + a); };
     auto nbr_full = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 4 + b); };
     auto nbr_empty = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 6 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 8);
+    const uint32_t peer_done = bar_base + 8u * (4 * C::STAGES + 8);               // leader: peer's partial sums are in L2
+    const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 9);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + (tmem_slot - base));
 
+    const long long t_start = p.trace ? clock64() : 0;
     pdl_launch_dependents();      // the next layer may be scheduled as this grid's CTAs retire
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops on the
+    // uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // Tap packing: a chunk is 64 K-columns = `tpg` taps of `cin` stored channels each (cin 8/16/32 -> 8/4/2 taps per
     // chunk), so the narrow early layers run 4/7/14 chunks per tile instead of 27.  The weight pack has the same
     // K order (sassd_spconv_pack).
-    const int ppt = p.cin >> 3;                              // 16-byte pieces per tap
-    const int tpg = (BKC % p.cin == 0) ? BKC / p.cin : 1;    // taps per chunk
+    const int cin = CS ? CS : p.cin;
+    const int ppt = cin >> 3;                                // 16-byte pieces per tap
+    const int tpg = (BKC % cin == 0) ? BKC / cin : 1;        // taps per chunk
     const int nchunks = (p.taps + tpg - 1) / tpg;
     const bool nbr_tiles = TABLE && p.taps <= 27;
-    const bool helper_fence = !(p.dbg & 128);
+    const uint32_t all_taps = p.taps >= 32 ? 0xffffffffu : ((1u << p.taps) - 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -104,6 +166,7 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS); }
         for (int b = 0; b < 2; ++b) { mbar_init(nbr_full(b), 1); mbar_init(nbr_empty(b), PROD_WARPS); }
+        mbar_init(peer_done, EPI_WARPS * 32);
         fence_barrier_init();
     }
     if (warp == W_MMA) {
@@ -114,11 +177,29 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();           // the peer's barriers exist before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_wait();                   // producing layer / rulebook complete; nothing above touched global data
     const int M = p.d_rows ? min(__ldg(p.d_rows), p.rows_cap) : p.rows_cap;
     const int ntiles = (M + BM - 1) / BM;
+    long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+    if (tr && threadIdx.x == 0) { tr[0] = t_start; tr[1] = clock64(); }
+    // Work decomposition, uniform over the grid.  Tap split: cluster q owns tile q, its two CTAs share the chunks.
+    const uint32_t crank = cluster_ctarank();
+    const bool split = TABLE && p.scratch && !(p.dbg & 2) && nchunks > 1 && 2 * ntiles <= (int)gridDim.x &&
+                       ntiles <= SPLIT_TILES_MAX;
+    const int tile0 = split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstep = split ? ntiles : (int)gridDim.x;        // split: at most one tile per cluster
+    const int part = split ? (int)crank : 0, nparts = split ? 2 : 1;
+    auto chunks_of = [&](int tile) {
+        uint32_t tm = all_taps;
+        if (TABLE && p.tile_mask && !(p.dbg & 1)) {
+            tm = (uint32_t)__ldg(&p.tile_mask[tile]) & all_taps;
+            if (!tm) tm = 1u;       // a tile without any pair still has to produce act(shift): run one (all-zero) chunk
+        }
+        return ChunkSet(tm, tpg, nchunks, part, nparts).mask;
+    };
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ===================== A producers: cp.async gather of split rows =====================
@@ -132,51 +213,72 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         uint32_t phase = 0;
         int nb = 0;                    // neighbour-table buffer of this tile
         uint32_t nb_phase = 0;
-        int tchunk = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        long long tw = 0, ti = 0, tn = 0;
+        const bool trp = tr && pt == 0;
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
             const int m = tile * BM + r;
             // rows of the table the loader thread copied for this tile (whole 16-byte units only)
             const int rows_here = min(BM, p.rows_cap - tile * BM);
             const int rows_copied = nbr_tiles ? ((rows_here * p.taps * 4) & ~15) / (p.taps * 4) : 0;
             const int* nrow = nbr_smem + nb * (C::NBR_TILE_BYTES / 4) + r * p.taps;
             const bool from_smem = nbr_tiles && r < rows_copied;
+            const uint32_t cmask = chunks_of(tile);
+            long long c0 = trp ? clock64() : 0;
             if (nbr_tiles) {
                 if (lane == 0) mbar_wait(nbr_full(nb), nb_phase);
                 __syncwarp();
             }
+            if (trp) tn += clock64() - c0;
             for (int g = 0; g < nchunks; ++g) {
-                const bool tr = (p.dbg & 64) && blockIdx.x == 0 && pt == 0 && tchunk < TRACE_CHUNKS;
-                long long ts0 = 0, ts1 = 0;
-                if (tr) ts0 = clock64();
+                if (!((cmask >> g) & 1u)) continue;
                 // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
                 // word slow every other barrier operation of the CTA)
+                c0 = trp ? clock64() : 0;
                 if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
                 __syncwarp();
-                if (tr) ts1 = clock64();
+                const long long c1 = trp ? clock64() : 0;
                 const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
                 if (!(p.dbg & 32)) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int q = hf * 4 + c;                        // 16-byte piece (8 K-columns) of the row
-                        const int tl = q / ppt, piece = q - tl * ppt;    // tap within the chunk, piece within the tap
-                        const int t = g * tpg + tl;
-                        int src = -1;
-                        if (m < M && tl < tpg && t < p.taps)
-                            src = TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
+                    // This thread owns pieces q = 4*hf .. 4*hf+3 (8 K-columns each) of row r: piece -> (tap within the
+                    // chunk, piece within the tap) is compile-time for CS = 64 / 32 / 16 / 8.
+                    auto row_of = [&](int t) -> int {
+                        if (m >= M || t >= p.taps) return -1;
+                        return TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
+                    };
+                    auto copy = [&](int q, int src, int piece) {
                         const uint32_t nbytes = src >= 0 ? 16u : 0u;     // 0 -> hardware zero fill
-                        const __half* sp = p.in + (size_t)(src < 0 ? 0 : src) * p.cin + (nbytes ? piece * 8 : 0);
+                        const __half* sp = p.in + (size_t)(src < 0 ? 0 : src) * cin + (nbytes ? piece * 8 : 0);
                         const uint32_t off = ((uint32_t)q ^ sw) << 4;
                         cp_async16(a_hi + off, sp, nbytes);
                         cp_async16(a_lo + off, sp + p.in_plane, nbytes);
+                    };
+                    if constexpr (CS == 64 || CS == 32) {          // one tap per thread: tl = 0 (64) or hf (32)
+                        const int tl = CS == 64 ? 0 : hf;
+                        const int src = row_of(g * tpg + tl);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) copy(hf * 4 + c, src, CS == 64 ? hf * 4 + c : c);
+                    } else if constexpr (CS == 16) {               // two taps per thread, two pieces each
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int src = row_of(g * 4 + hf * 2 + h);
+                            copy(hf * 4 + h * 2, src, 0);
+                            copy(hf * 4 + h * 2 + 1, src, 1);
+                        }
+                    } else if constexpr (CS == 8) {                // four taps per thread, one piece each
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) copy(hf * 4 + c, row_of(g * 8 + hf * 4 + c), 0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int q = hf * 4 + c;
+                            const int tl = q / ppt, piece = q - tl * ppt;
+                            copy(q, tl < tpg ? row_of(g * tpg + tl) : -1, piece);
+                        }
                     }
                 }
                 cp_async_arrive_noinc(full_a(stage));
+                if (trp) { tw += c1 - c0; ti += clock64() - c1; }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-                if (tr) {
-                    long long* q = p.trace + (size_t)(0 * TRACE_CHUNKS + tchunk) * 4;
-                    q[0] = ts0; q[1] = ts1; q[2] = clock64(); q[3] = 0;
-                }
-                ++tchunk;
             }
             if (nbr_tiles) {
                 __syncwarp();
@@ -184,12 +286,13 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                 if (++nb == 2) { nb = 0; nb_phase ^= 1u; }
             }
         }
+        if (trp) { tr[2] = tw; tr[3] = ti; tr[4] = tn; tr[5] = clock64(); }
     } else if (warp == W_BLOAD) {
         // ===================== weights + neighbour-table tiles (bulk copies) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int nb = 0, issued = 0;
+            int nb = 0;
             uint32_t nb_phase = 0;
             auto load_nbr = [&](int tile) {     // one bulk copy: the tile's rows of the table are contiguous
                 const int rows_here = min(BM, p.rows_cap - tile * BM);
@@ -199,27 +302,17 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                 if (bytes) bulk_g2s(nbr_base + nb * C::NBR_TILE_BYTES, p.nbr + (size_t)tile * BM * p.taps, bytes, nbr_full(nb));
                 if (++nb == 2) { nb = 0; nb_phase ^= 1u; }
             };
-            if (nbr_tiles && (int)blockIdx.x < ntiles) load_nbr(blockIdx.x);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                if (nbr_tiles && tile + (int)gridDim.x < ntiles) load_nbr(tile + gridDim.x);
+            if (nbr_tiles && tile0 < ntiles) load_nbr(tile0);
+            for (int tile = tile0; tile < ntiles; tile += tstep) {
+                if (nbr_tiles && tile + tstep < ntiles) load_nbr(tile + tstep);
+                const uint32_t cmask = chunks_of(tile);
                 for (int ch = 0; ch < nchunks; ++ch) {
-                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && issued < TRACE_CHUNKS;
-                    long long ts0 = 0;
-                    if (tr) ts0 = clock64();
+                    if (!((cmask >> ch) & 1u)) continue;
                     mbar_wait(empty(stage), phase ^ 1u);
-                    if (tr) {
-                        long long* q = p.trace + (size_t)(1 * TRACE_CHUNKS + issued) * 4;
-                        q[0] = ts0; q[1] = clock64(); q[2] = 0; q[3] = 0;
-                    }
                     const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
                     const uint8_t* src = (const uint8_t*)p.wpack + (size_t)ch * (2 * C::B_TILE_BYTES);
-                    if ((p.dbg & 8) && issued >= C::STAGES) {
-                        mbar_expect_tx(full_b(stage), 0);
-                    } else {
-                        mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
-                        bulk_g2s(dst, src, 2 * C::B_TILE_BYTES, full_b(stage));
-                    }
-                    ++issued;
+                    mbar_expect_tx(full_b(stage), 2 * C::B_TILE_BYTES);
+                    bulk_g2s(dst, src, 2 * C::B_TILE_BYTES, full_b(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -229,12 +322,14 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         // The producers write shared memory through the generic proxy (cp.async), tcgen05.mma reads it through the
         // async proxy, so a fence.proxy.async has to sit between.  In the producers it lowers to MEMBAR.ALL.CTA and
         // stalls on their own in-flight copies; in the MMA lane it costs 130-650 clk per chunk that are serial with
-        // MMA issue (timeline trace).  This lane has nothing else to do.
-        if (lane == 0 && helper_fence) {
+        // MMA issue (round-1 timeline trace).  This lane has nothing else to do.
+        if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < ntiles; tile += tstep) {
+                const uint32_t cmask = chunks_of(tile);
                 for (int ch = 0; ch < nchunks; ++ch) {
+                    if (!((cmask >> ch) & 1u)) continue;
                     mbar_wait(full_a(stage), phase);
                     fence_proxy_async();
                     mbar_arrive(ready_a(stage));
@@ -243,56 +338,70 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
             }
         }
     } else if (warp == W_MMA) {
-        if (lane == 0) {
-            // x*w = ah*bh + (ah*bl + al*bh)/2048 as TWO instructions per K=16 step: ah x [bh | bl] (N = 2*BN, the
-            // weight block's hi and lo rows are contiguous) -> big and small1, al x bh (N = BN) -> small2.  An SS-mode
-            // MMA is paced by its operand reads (~64 B/clk: 4 KB of A + 32 B per B row), so sharing the A read between
-            // two of the three products takes 22 % off the tensor time (measured 96 clk per 128x64x16 instruction).
-            constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN, 0u /*F16*/), idesc1 = make_idesc(BM, BN, 0u);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0, tchunk = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
+        // ===================== MMA issue: warp-convergent loop, one elected lane issues =====================
+        // x*w = ah*bh + (ah*bl + al*bh)/2048 as TWO instructions per K=16 step: ah x [bh | bl] (N = 2*BN, the weight
+        // block's hi and lo rows are contiguous) -> big and small1, al x bh (N = BN) -> small2.
+        constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN, 0u /*F16*/), idesc1 = make_idesc(BM, BN, 0u);
+        constexpr uint32_t kStageLo = (uint32_t)C::STAGE_BYTES >> 4, kTileLo = (uint32_t)A_TILE_BYTES >> 4;
+        const bool leader = elect_one();
+        const uint32_t lo0 = desc_lo(base);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int executed = 0, tiles_done = 0;
+        long long mw = 0, mi = 0, me = 0;
+        const bool trm = tr && leader;
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
+            const uint32_t cmask = chunks_of(tile);
+            long long c0 = trm ? clock64() : 0;
+            mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            if (trm) me += clock64() - c0;
+            const uint32_t d_big = tmem_base + (uint32_t)(acc * C::ACC_COLS), d_small2 = d_big + (uint32_t)(2 * BN);
+            uint32_t accum = 0u;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                if (!((cmask >> ch) & 1u)) continue;
+                c0 = trm ? clock64() : 0;
+                mbar_wait(ready_a(stage), phase);
+                mbar_wait(full_b(stage), phase);
                 tc_fence_after();
-                const uint32_t d_big = tmem_base + (uint32_t)(acc * C::ACC_COLS), d_small2 = d_big + (uint32_t)(2 * BN);
-                for (int ch = 0; ch < nchunks; ++ch) {
-                    const bool tr = (p.dbg & 64) && blockIdx.x == 0 && tchunk < TRACE_CHUNKS;
-                    long long ts0 = 0, ts1 = 0, ts2 = 0;
-                    if (tr) ts0 = clock64();
-                    if (helper_fence) {
-                        mbar_wait(ready_a(stage), phase);
+                const long long c1 = trm ? clock64() : 0;
+                // channels beyond cin are zero in both operands: issue only the K=16 steps that carry data
+                const int ksteps = (p.dbg & 16) ? 0 : min(4, (min(tpg, p.taps - ch * tpg) * cin + 15) / 16);
+                const uint32_t ah = lo0 + (uint32_t)stage * kStageLo, al = ah + kTileLo, bh = al + kTileLo;
+                if (leader) {
+                    if (ksteps == 4) {          // the common case, straight-line
+                        mma_f16_lo(d_big, ah, bh, idesc2, accum);
+                        mma_f16_lo(d_small2, al, bh, idesc1, accum);
+#pragma unroll
+                        for (uint32_t k = 1; k < 4; ++k) {
+                            mma_f16_lo(d_big, ah + k * kDescK16, bh + k * kDescK16, idesc2, 1u);
+                            mma_f16_lo(d_small2, al + k * kDescK16, bh + k * kDescK16, idesc1, 1u);
+                        }
                     } else {
-                        mbar_wait(full_a(stage), phase);
-                        fence_proxy_async();
-                    }
-                    if (tr) ts1 = clock64();
-                    mbar_wait(full_b(stage), phase);
-                    tc_fence_after();
-                    if (tr) ts2 = clock64();
-                    const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;      // b_lo follows at + B_TILE_BYTES
-                    // channels beyond cin are zero in both operands: issue only the K=16 steps that carry data
-                    const int ksteps = (p.dbg & 16) ? 0 : min(4, (min(tpg, p.taps - ch * tpg) * p.cin + 15) / 16);
-                    for (int k16 = 0; k16 < ksteps; ++k16) {
-                        const uint32_t ko = (uint32_t)k16 * 32u;
-                        const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko), db = make_desc(b_hi + ko);
-                        const uint32_t accum = (ch | k16) ? 1u : 0u;
-                        mma_f16(d_big, dah, db, idesc2, accum);
-                        mma_f16(d_small2, dal, db, idesc1, accum);
+                        for (int k = 0; k < ksteps; ++k) {
+                            mma_f16_lo(d_big, ah + (uint32_t)k * kDescK16, bh + (uint32_t)k * kDescK16, idesc2, k ? 1u : accum);
+                            mma_f16_lo(d_small2, al + (uint32_t)k * kDescK16, bh + (uint32_t)k * kDescK16, idesc1, k ? 1u : accum);
+                        }
                     }
                     mma_commit(empty(stage));
-                    if (tr) {
-                        long long* q = p.trace + (size_t)(2 * TRACE_CHUNKS + tchunk) * 4;
-                        q[0] = ts0; q[1] = ts1; q[2] = ts2; q[3] = clock64();
-                    }
-                    ++tchunk;
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit(tmem_full(acc));
-                if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
+                __syncwarp();
+                if (trm) { mw += c1 - c0; mi += clock64() - c1; }
+                if (ksteps) accum = 1u;
+                ++executed;
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
+            if (leader) mma_commit(tmem_full(acc));
+            __syncwarp();
+            ++tiles_done;
+            if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (trm) { tr[6] = mw; tr[7] = mi; tr[8] = me; tr[9] = clock64(); tr[10] = executed; }
+        if (p.counters && leader && executed) {
+            atomicAdd(&p.counters[0], executed);
+            atomicAdd(&p.counters[1], part == 0 ? tiles_done : 0);
         }
     } else {
         // ===================== epilogue =====================
@@ -300,24 +409,57 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
         const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
-            __syncwarp();
-            tc_fence_after();
+        for (int tile = tile0; tile < ntiles; tile += tstep) {
+            const uint32_t cmask = chunks_of(tile);
+            const bool have_acc = cmask != 0;       // a split peer may have been dealt no chunk at all
+            if (have_acc) {
+                if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
+                __syncwarp();
+                tc_fence_after();
+            }
             const int m = tile * BM + r;
+            float* prow = split ? p.scratch + ((size_t)tile * BM + r) * BN : nullptr;
+            if (split && part == 0) {           // leader: the peer's partial sums must be visible
+                if (lane == 0) mbar_wait_cluster(peer_done, 0u);
+                __syncwarp();
+            }
             constexpr int CW = 16;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += CW) {
                 uint32_t v[CW], u[CW], w[CW];
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + c0);
-                tmem_ld<CW>(v, taddr);
-                tmem_ld<CW>(u, taddr + (uint32_t)BN);
-                tmem_ld<CW>(w, taddr + (uint32_t)(2 * BN));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + CW >= BN) {      // accumulators are in registers: release the buffer to the MMA lane
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty(acc));
+                if (have_acc) {
+                    tmem_ld<CW>(v, taddr);
+                    tmem_ld<CW>(u, taddr + (uint32_t)BN);
+                    tmem_ld<CW>(w, taddr + (uint32_t)(2 * BN));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c0 + CW >= BN) {      // accumulators are in registers: release the buffer to the MMA lane
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty(acc));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = u[j] = w[j] = 0u;
+                }
+                float a[CW];
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    const float small = __fadd_rn(__uint_as_float(u[j]), __uint_as_float(w[j]));
+                    a[j] = __fadd_rn(__uint_as_float(v[j]), small * (1.f / kF16LoScale));
+                }
+                if (split && part != 0) {       // peer: hand the partial sums over, no epilogue
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4) *(float4*)(prow + c0 + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                    continue;
+                }
+                if (split) {
+#pragma unroll
+                    for (int j = 0; j < CW; j += 4) {
+                        const float4 q = __ldcg((const float4*)(prow + c0 + j));     // L2 (the peer's SM wrote it)
+                        a[j] = __fadd_rn(a[j], q.x); a[j + 1] = __fadd_rn(a[j + 1], q.y);
+                        a[j + 2] = __fadd_rn(a[j + 2], q.z); a[j + 3] = __fadd_rn(a[j + 3], q.w);
+                    }
                 }
                 if (m < M) {
                     float o[CW];
@@ -347,8 +489,7 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                         const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float small = __fadd_rn(__uint_as_float(u[j + e]), __uint_as_float(w[j + e]));
-                            float val = fmaf(__fadd_rn(__uint_as_float(v[j + e]), small * (1.f / kF16LoScale)), scs[e], shs[e]);
+                            float val = fmaf(a[j + e], scs[e], shs[e]);
                             if (p.relu) val = fmaxf(val, 0.f);
                             o[j + e] = (n + e) < p.cout ? val : 0.f;
                         }
@@ -379,8 +520,10 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
                     }
                 }
             }
-            if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
+            if (split && part != 0) mbar_arrive_remote(peer_done, 0u);     // every thread releases its own stores
+            if (have_acc && ++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
+        if (tr && threadIdx.x == 0) tr[11] = clock64();
     }
 
     tc_fence_before();
@@ -390,30 +533,52 @@ __global__ void __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                      : "memory");
     }
+    cluster_sync_all();           // no CTA of the cluster exits while its peer may still arrive on its barriers
 }
 
-template <int TABLE, int BN>
+template <int TABLE, int BN, int CS>
 static int launch3(const Args& a, cudaStream_t stream) {
     using C = Cfg3<BN>;
-    auto kern = spconv_split_kernel<TABLE, BN>;
-    static bool configured = false;
-    if (!configured) {
+    auto kern = spconv_split_kernel<TABLE, BN, CS>;
+    // Persistent CTAs in clusters of two, one CTA per SM (225 KB of shared memory): the grid must not exceed what is
+    // co-resident - GPCs with an odd number of free SMs cannot host a last cluster, and a cluster left over for a
+    // second wave would double the kernel's time.
+    static int max_ctas = 0;
+    if (!max_ctas) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
             return SASSD_ERR_LAUNCH;
-        configured = true;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(148); cfg.blockDim = dim3(THREADS3); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+            cudaGetLastError();
+            clusters = 64;
+        }
+        max_ctas = CLUSTER * (clusters < 74 ? clusters : 74);
     }
-    int grid = sassd_div_up(a.rows_cap, BM);
-    if (grid > 148) grid = 148;
+    // one CTA per tile up to the resident CTAs; with a tap split two CTAs per tile; always whole clusters
+    int grid = CLUSTER * sassd_div_up(a.rows_cap, BM);
+    if (grid > max_ctas) grid = max_ctas;
     if (launch_pdl(kern, dim3(grid), dim3(THREADS3), C::SMEM_BYTES, stream, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
 }
 
+// the network's (stored cin, cout) shapes get compile-time producers; anything else the run-time ones
 template <int TABLE>
 static int dispatch3(const Args& a, cudaStream_t s) {
-    if (a.cout <= 16) return launch3<TABLE, 16>(a, s);
-    if (a.cout <= 32) return launch3<TABLE, 32>(a, s);
-    if (a.cout <= 64) return launch3<TABLE, 64>(a, s);
-    return SASSD_ERR_UNSUPPORTED;
+    const int bn = a.cout <= 16 ? 16 : (a.cout <= 32 ? 32 : 64);
+    if (a.cout > 64) return SASSD_ERR_UNSUPPORTED;
+    if (a.cin == 64 && bn == 64) return launch3<TABLE, 64, 64>(a, s);
+    if (TABLE) {
+        if (a.cin == 32 && bn == 64) return launch3<TABLE, 64, 32>(a, s);
+        if (a.cin == 32 && bn == 32) return launch3<TABLE, 32, 32>(a, s);
+        if (a.cin == 16 && bn == 32) return launch3<TABLE, 32, 16>(a, s);
+        if (a.cin == 16 && bn == 16) return launch3<TABLE, 16, 16>(a, s);
+        if (a.cin == 8 && bn == 16) return launch3<TABLE, 16, 8>(a, s);
+    }
+    if (bn == 16) return launch3<TABLE, 16, 0>(a, s);
+    if (bn == 32) return launch3<TABLE, 32, 0>(a, s);
+    return launch3<TABLE, 64, 0>(a, s);
 }
 
 }  // namespace sps
@@ -459,47 +624,58 @@ extern "C" int sassd_spconv_pack(const float* weight, int taps, int cin, int cin
     return sassd_check_launch();
 }
 
+extern "C" size_t sassd_spconv_workspace_bytes(void) {
+    // fp32 partial sums of the peer CTA for the tap split: SPLIT_TILES_MAX tiles x 128 rows x 64 columns
+    return (size_t)sps::SPLIT_TILES_MAX * sps::BM * 64 * sizeof(float);
+}
+
 extern "C" int sassd_spconv_f16x3(const sassd_spconv_desc* d, const void* in_split, const void* wpack,
-                                  const float* scale, const float* shift, const int32_t* nbr, const int32_t* d_rows,
-                                  void* out_split, float* out_f32, sassd_stream_t stream_) {
+                                  const float* scale, const float* shift, const int32_t* nbr,
+                                  const int32_t* tile_mask, const int32_t* d_rows, void* out_split, float* out_f32,
+                                  void* ws, size_t ws_bytes, int32_t* counters, sassd_stream_t stream_) {
     if (!d || !in_split || !wpack || (!out_split && !out_f32)) return SASSD_ERR_ARG;
     if (d->cin < 8 || (d->cin & 7) || d->cin > 64 || d->cout < 1 || d->cout > 64 || d->taps < 1 || d->rows_cap < 0)
         return SASSD_ERR_ARG;
     if (d->taps > 1 && !nbr) return SASSD_ERR_ARG;
+    if (tile_mask && d->taps > 27) return SASSD_ERR_ARG;
     if (out_split && ((d->out_ch & 7) || d->out_ch < d->cout)) return SASSD_ERR_ARG;
     if (out_f32 && (d->out_f32_stride & 3)) return SASSD_ERR_ARG;
+    if (ws && ws_bytes < sassd_spconv_workspace_bytes()) return SASSD_ERR_WORKSPACE;
     if (d->rows_cap == 0) return SASSD_OK;
     sps::Args a;
     a.in = (const __half*)in_split; a.in_plane = (size_t)d->in_rows_cap * d->cin;
-    a.wpack = wpack; a.scale = scale; a.shift = shift; a.nbr = nbr; a.d_rows = d_rows;
+    a.wpack = wpack; a.scale = scale; a.shift = shift; a.nbr = nbr; a.tile_mask = tile_mask; a.d_rows = d_rows;
     a.out_split = (__half*)out_split; a.out_plane = (size_t)d->rows_cap * d->out_ch; a.out_f32 = out_f32;
+    a.scratch = (float*)ws; a.counters = counters;
     a.cin = d->cin; a.cout = d->cout; a.taps = d->taps; a.rows_cap = d->rows_cap; a.relu = d->relu;
     a.out_ch = d->out_ch; a.out_f32_stride = d->out_f32_stride;
     static const int dbg = [] { const char* e = getenv("SASSD_SPS_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     a.trace = nullptr;
-    if (dbg & 64) {      // timing experiment: dump CTA 0's per-chunk clock stamps of this launch to stderr
+    static const int trace_call = [] { const char* e = getenv("SASSD_SPS_TRACE"); return e ? atoi(e) : 0; }();
+    if (trace_call && d->taps > 1) {      // timing experiment: per-CTA clock sums of the trace_call-th ruled launch -> stderr
         static long long* trace = nullptr;
-        const size_t n = (size_t)3 * sps::TRACE_CHUNKS * 4;
-        if (!trace) cudaMalloc(&trace, n * sizeof(long long));
-        cudaMemsetAsync(trace, 0, n * sizeof(long long), (cudaStream_t)stream_);
-        a.trace = trace;
-        const int rc = d->taps > 1 ? sps::dispatch3<1>(a, (cudaStream_t)stream_) : sps::dispatch3<0>(a, (cudaStream_t)stream_);
         static int calls = 0;
-        if (rc == SASSD_OK && d->taps > 1 && d->rows_cap >= 1024 && ++calls == 3) {
+        const size_t n = (size_t)148 * 16;
+        if (!trace) cudaMalloc(&trace, n * sizeof(long long));
+        if (++calls == trace_call) {
+            cudaMemsetAsync(trace, 0, n * sizeof(long long), (cudaStream_t)stream_);
+            a.trace = trace;
+            const int rc = sps::dispatch3<1>(a, (cudaStream_t)stream_);
             std::vector<long long> h(n);
             cudaStreamSynchronize((cudaStream_t)stream_);
             cudaMemcpy(h.data(), trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
-            long long t0 = 0;
-            for (size_t i = 0; i < n; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
-            for (int ag = 0; ag < 3; ++ag)
-                for (int c = 0; c < sps::TRACE_CHUNKS; ++c) {
-                    const long long* q = &h[((size_t)ag * sps::TRACE_CHUNKS + c) * 4];
-                    fprintf(stderr, "TRACE %d %d %lld %lld %lld %lld\n", ag, c, q[0] ? q[0] - t0 : -1, q[1] ? q[1] - t0 : -1,
-                            q[2] ? q[2] - t0 : -1, q[3] ? q[3] - t0 : -1);
-                }
+            fprintf(stderr, "SPS_TRACE rows_cap %d cin %d cout %d: cta  prologue  kernel | prod: wait_empty issue wait_nbr end | "
+                            "mma: wait_data issue wait_acc end chunks | epi_end\n", d->rows_cap, d->cin, d->cout);
+            for (int c = 0; c < 148; c += (c < 4 ? 1 : 37)) {
+                const long long* q = &h[(size_t)c * 16];
+                if (!q[0]) continue;
+                fprintf(stderr, "SPS_TRACE %3d %8lld %8lld | %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld %4lld | %8lld\n", c,
+                        q[1] - q[0], (q[11] ? q[11] : q[9]) - q[0], q[2], q[3], q[4], q[5] ? q[5] - q[0] : 0, q[6], q[7], q[8],
+                        q[9] ? q[9] - q[0] : 0, q[10], q[11] ? q[11] - q[0] : 0);
+            }
+            return rc;
         }
-        return rc;
     }
     return d->taps > 1 ? sps::dispatch3<1>(a, (cudaStream_t)stream_) : sps::dispatch3<0>(a, (cudaStream_t)stream_);
 }

@@ -94,6 +94,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+// The MMA-issuing lane is an instruction-issue bottleneck long before the tensor pipe is (round-2 probe,
+// profiles/r2_mma_issue_probe.md: ~6-8 clk per SASS instruction in that single-thread stream, so a loop that rebuilds
+// three 64-bit descriptors per K step - ~20 instructions per UTCHMMA - runs at 100-130 clk per MMA against a 32-64
+// clk tensor floor).  Hence: the constant high word and the per-tile low word of a descriptor are split, a K=16 step
+// is "+2" on the low word (32 bytes >> 4; the 14-bit address field cannot carry, shared memory is < 256 KB), and the
+// issue loops are fully unrolled around these.
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescK16 = 2u;      // low-word advance per K=16 step of fp16 operands (32 bytes)
+
+// whole-warp convergent election (CUTLASS' elect_one_sync): exactly one lane gets true, always the same one
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -116,6 +138,52 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
+}
+// kind::f16 with descriptors given as low words (high word = kDescHi); ACCUM is a compile-time flag where known
+__device__ __forceinline__ void mma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+}
+// MODE 0 plain, 1 = fill collector b0 with B, 2 = last use of b0 (weight-stationary form, see mma_f16_ws)
+template <int MODE>
+__device__ __forceinline__ void mma_f16_ws_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    if constexpr (MODE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\t"
+                     "mov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
+    else if constexpr (MODE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\t"
+                     "mov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\t"
+                     "mov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.ws.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
+}
+// A-collector forms: MODE 1 = keep A after this MMA (fill), 2 = take A from the collector (lastuse)
+template <int MODE>
+__device__ __forceinline__ void mma_f16_acoll_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+    if constexpr (MODE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\t"
+                     "mov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\t"
+                     "mov.b64 db, {%2, %5};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+                     "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi) : "memory");
 }
 // Same instruction with the A-operand collector: `keep` leaves A in the tensor core's collector buffer after this
 // MMA, `reuse` takes A from there instead of reading shared memory again (SASS: UTCHMMA ... A_KEEP / A_REUSE).

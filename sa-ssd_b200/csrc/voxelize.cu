@@ -47,36 +47,59 @@ vox_insert_kernel(const float4* __restrict__ points, const int* __restrict__ pt_
     __syncthreads();
     const int n = s_off[batch];
     const uint32_t mask = (uint32_t)slots - 1u;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(&points[i]);
-        // fp32 subtract, IEEE divide, floor — exactly numba's float32 arithmetic (points_ops.py:31)
-        const float cx = floorf(__fdiv_rn(__fsub_rn(p.x, P.lo[0]), P.vs[0]));
-        const float cy = floorf(__fdiv_rn(__fsub_rn(p.y, P.lo[1]), P.vs[1]));
-        const float cz = floorf(__fdiv_rn(__fsub_rn(p.z, P.lo[2]), P.vs[2]));
-        // (c < 0 || c >= grid) rejects; non-finite coordinates are rejected too (the
-        // reference's behaviour is undefined there: NaN passes both tests and is cast to int)
-        const bool ok = (cx >= 0.f) && (cx < (float)P.grid[0]) && (cy >= 0.f) && (cy < (float)P.grid[1]) &&
-                        (cz >= 0.f) && (cz < (float)P.grid[2]);
-        int slot = -1;
-        if (ok) {
-            const int b = vox_frame_of(s_off, batch, i);
-            const int cell = ((int)cz * P.grid[1] + (int)cy) * P.grid[0] + (int)cx;
-            int* fk = keys + (size_t)b * slots;
-            // bounded probe: the table holds >= 2x the frame's points, so this always terminates early
-            uint32_t s = sassd_hash32((uint32_t)cell) & mask;
-            int probes = 0;
-            while (true) {
-                int prev = atomicCAS(&fk[s], SASSD_EMPTY_KEY, cell);
-                if (prev == SASSD_EMPTY_KEY || prev == cell) { slot = b * slots + (int)s; break; }
-                s = (s + 1) & mask;
-                if (++probes >= slots) { atomicOr(status, SASSD_FLAG_HASH_FULL); break; }
-            }
-            if (slot >= 0) {
-                atomicMin(&first[slot], i);
-                pt_next[i] = atomicExch(&head[slot], i);
+    const int lane = threadIdx.x & 31;
+    // Warp-aggregated insertion: the loop is warp-uniform (a warp owns 32 consecutive points - in a real Velodyne file
+    // consecutive returns of a beam mostly share a voxel).  Lanes whose points fall into the same cell of the same
+    // frame find each other with __match_any_sync; only the group's lowest lane probes the table (one atomicCAS chain
+    // per distinct cell instead of one per point), takes the atomicMin for the group (it holds the smallest index) and
+    // the group enters the slot's list as one pre-linked chain with a single atomicExch.
+    for (int base_i = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base_i < n; base_i += gridDim.x * blockDim.x) {
+        const int i = base_i + lane;
+        bool ok = false;
+        int b = 0, cell = 0;
+        if (i < n) {
+            const float4 p = __ldg(&points[i]);
+            // fp32 subtract, IEEE divide, floor — exactly numba's float32 arithmetic (points_ops.py:31)
+            const float cx = floorf(__fdiv_rn(__fsub_rn(p.x, P.lo[0]), P.vs[0]));
+            const float cy = floorf(__fdiv_rn(__fsub_rn(p.y, P.lo[1]), P.vs[1]));
+            const float cz = floorf(__fdiv_rn(__fsub_rn(p.z, P.lo[2]), P.vs[2]));
+            // (c < 0 || c >= grid) rejects; non-finite coordinates are rejected too (the
+            // reference's behaviour is undefined there: NaN passes both tests and is cast to int)
+            ok = (cx >= 0.f) && (cx < (float)P.grid[0]) && (cy >= 0.f) && (cy < (float)P.grid[1]) &&
+                 (cz >= 0.f) && (cz < (float)P.grid[2]);
+            if (ok) {
+                b = vox_frame_of(s_off, batch, i);
+                cell = ((int)cz * P.grid[1] + (int)cy) * P.grid[0] + (int)cx;
             }
         }
-        pt_slot[i] = slot;
+        int slot = -1;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            // a warp's 32 points span at most two frames in practice; the frame goes into the match key's top bits
+            const unsigned long long key = ((unsigned long long)(unsigned)b << 32) | (unsigned)cell;
+            const unsigned peers = __match_any_sync(okmask, key);
+            const int leader = __ffs(peers) - 1;
+            if (lane == leader) {
+                int* fk = keys + (size_t)b * slots;
+                // bounded probe: the table holds >= 2x the frame's points, so this always terminates early
+                uint32_t s = sassd_hash32((uint32_t)cell) & mask;
+                int probes = 0;
+                while (true) {
+                    int prev = atomicCAS(&fk[s], SASSD_EMPTY_KEY, cell);
+                    if (prev == SASSD_EMPTY_KEY || prev == cell) { slot = b * slots + (int)s; break; }
+                    s = (s + 1) & mask;
+                    if (++probes >= slots) { atomicOr(status, SASSD_FLAG_HASH_FULL); break; }
+                }
+                if (slot >= 0) atomicMin(&first[slot], i);       // lowest lane = smallest point index of the group
+            }
+            slot = __shfl_sync(peers, slot, leader);
+            if (slot >= 0) {
+                const unsigned higher = peers & ~((2u << lane) - 1u);
+                if (higher) pt_next[i] = base_i + (__ffs(higher) - 1);                 // next point of the group
+                else pt_next[i] = atomicExch(&head[slot], base_i + leader);           // tail -> old head; head -> group
+            }
+        }
+        if (i < n) pt_slot[i] = slot;
     }
 }
 

@@ -38,6 +38,10 @@ class SingleStageDetector(nn.Module):
         self.anchor_set = None
         self._pinned = None
         self._mask_stream = None
+        self._graph = None
+        self._graph_args = None
+        self._stream_slots = None
+        self._stream_key = None
         if isinstance(pretrained, str):
             from .checkpoint import load_params_from_file
             load_params_from_file(self, pretrained)
@@ -48,14 +52,28 @@ class SingleStageDetector(nn.Module):
         return hasattr(self, "rpn_head") and self.rpn_head is not None
 
     def set_precision(self, precision, sparse=None):
-        """ops.PREC_FP32 = CUDA-core FFMA kernels, ops.PREC_TF32X3 = tcgen05 tensor-core kernels (3xTF32 split,
-        fp32-accurate).  ``sparse`` optionally selects a different path for the 13 ruled sparse convs."""
+        """ops.PREC_F16X3 (default) = tcgen05 tensor-core kernels on the fp32-accurate 3xFP16 operand split
+        (TMA-fed dense convs, cp.async-fed sparse convs); ops.PREC_TF32X3 = the 3xTF32 tcgen05 kernels;
+        ops.PREC_FP32 = CUDA-core FFMA kernels (bisecting / accuracy yard-stick).  ``sparse`` optionally selects a
+        different path for the 13 ruled sparse convs."""
         self.neck.set_precision(precision, sparse)
         self.rpn_head.precision = precision
         self.extra_head.precision = precision
+        self._drop_captured_graphs()
+
+    def _drop_captured_graphs(self):
+        """Captured steps bake in the device addresses of packed weights, folded BN vectors and layer constants and
+        the kernel selection; anything that changes those must force a re-capture."""
+        self._graph = None
+        self._stream_slots = None
+        self._stream_key = None
 
     def refresh_packed_weights(self):
-        pass  # packed/folded tensors are version-checked on use
+        """Called after parameters were (re)loaded (checkpoint.load_state_dict_into).  Packed / folded tensors are
+        version-checked on eager use, but a CUDA-graph replay never re-checks: drop every captured step (the
+        single-step graph of enable_cuda_graph and the detect_stream slots) so the next call re-captures with the
+        new weights."""
+        self._drop_captured_graphs()
 
     # ------------------------------------------------------------------ reference-signature path
     def merge_second_batch(self, batch_args):
@@ -81,9 +99,10 @@ class SingleStageDetector(nn.Module):
         return self.forward_test(img, img_meta, **kwargs)
 
     def forward_test(self, img, img_meta, **kwargs):
-        """single_stage.py:110-131.  Returns, per frame, a dict(boxes_lidar [D,7], scores [D],
-        label_preds [D]) — the inputs of kitti_bbox2results (transforms.py:225-279), which needs
-        the KITTI calibration and is the next row of the port."""
+        """single_stage.py:110-131.  When every ``img_meta`` carries the KITTI calibration (``calib``) and the
+        caller set ``class_names`` (tools/test.py:139) the return value is the reference's: the list of KITTI
+        annotation dicts of ``kitti_bbox2results`` (transforms.py:225-279).  Without calibration (synthetic clouds)
+        it returns, per frame, the inputs of that conversion: dict(boxes_lidar [D,7], scores [D], label_preds [D])."""
         ops.require_cuda()
         batch_size = len(img_meta)
         dev = next(self.parameters()).device
@@ -100,6 +119,10 @@ class SingleStageDetector(nn.Module):
         bbox_score = self.extra_head(conv6, guided_anchors, is_test=True)
         det_bboxes, det_scores, det_labels = self.extra_head.get_rescore_bboxes(
             guided_anchors, bbox_score, anchor_labels, img_meta, self.test_cfg.extra)
+        if self.class_names is not None and all(isinstance(m, dict) and m.get("calib") is not None for m in img_meta):
+            from .results import kitti_bbox2results
+            return [kitti_bbox2results(b, s, l, m, class_names=self.class_names)
+                    for b, s, l, m in zip(det_bboxes, det_scores, det_labels, img_meta)]
         return [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(det_bboxes, det_scores, det_labels)]
 
     # ------------------------------------------------------------------ fused raw-points path
@@ -154,11 +177,13 @@ class SingleStageDetector(nn.Module):
         """Capture forward_device once for (batch, max_points_per_frame) and replay it per step: every
         data-dependent size already lives on the device, so the ~65 launches of a step become one graph
         launch.  Steps whose shape does not fit fall back to the eager path."""
+        self._graph_args = (int(batch), int(max_points_per_frame))
         self._graph = _GraphedStep(self, batch, max_points_per_frame)
         return self._graph
 
     def disable_cuda_graph(self):
         self._graph = None
+        self._graph_args = None
 
     def detect_stream(self, batches, batch, max_points_per_frame=32768, depth=4, concurrent=True):
         """Throughput API: iterate over batches (each a list of ``batch`` raw point arrays) and yield their
@@ -168,7 +193,7 @@ class SingleStageDetector(nn.Module):
         step (voxelize, rulebooks, the sparse layers, NMS) run beside the dense layers of its neighbour."""
         ops.require_cuda()
         key = (batch, max_points_per_frame, depth)
-        if getattr(self, "_stream_key", None) != key:
+        if self._stream_key != key or self._stream_slots is None:
             self._stream_slots = [_GraphedStep(self, batch, max_points_per_frame) for _ in range(depth)]
             self._copy_stream = torch.cuda.Stream()
             self._stream_key = key
@@ -196,7 +221,9 @@ class SingleStageDetector(nn.Module):
             raise RuntimeError("call attach_data_pipeline(voxel_generator, anchor_set) first")
         dev = next(self.parameters()).device
         hp, ho, counts = self.stage_points(points_list)
-        g = getattr(self, "_graph", None)
+        if self._graph is None and self._graph_args is not None:     # dropped by a weight / precision change
+            self._graph = _GraphedStep(self, *self._graph_args)
+        g = self._graph
         if g is not None and not return_aux and g.fits(len(points_list), counts):
             bbs, scs, lbs = g.run_host(hp, ho, sum(counts))
             return [dict(boxes_lidar=b, scores=s, label_preds=l) for b, s, l in zip(bbs, scs, lbs)]

@@ -18,9 +18,11 @@ def init_from_env(backend=None):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            kw["device_id"] = torch.device("cuda", local)      # eager communicator creation, no lazy first-use cost
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
 
 
@@ -29,17 +31,43 @@ def shard_frames(n_frames, rank, world):
     return list(range(rank, n_frames, world))
 
 
+class DetectionGather:
+    """The shard's single exchange step: ONE all_gather_into_tensor of the fixed-size result
+    block [det | ndet] per rank into a pre-allocated buffer (the reference pickles per-rank result lists to a shared
+    file system, mmdet/core/evaluation/eval_hooks.py:92-106).  ``warm()`` runs the collective once so that
+    communicator / channel set-up is not inside anybody's timed region."""
+
+    def __init__(self, frames_local, det_cap, device):
+        self.F, self.cap, self.device = int(frames_local), int(det_cap), device
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.row = self.F * self.cap * 9 + self.F                  # floats per rank: det block + counts (as f32 bits)
+        self.send = torch.zeros((self.row,), dtype=torch.float32, device=device)
+        self.recv = torch.zeros((self.world * self.row,), dtype=torch.float32, device=device)
+
+    def warm(self):
+        self(torch.zeros((self.F, self.cap, 9), dtype=torch.float32, device=self.device),
+             torch.zeros((self.F,), dtype=torch.int32, device=self.device))
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def __call__(self, det, ndet):
+        """det [F, cap, 9] f32, ndet [F] i32 -> det [W, F, cap, 9], ndet [W, F] on every rank
+        (frame (r, j) is global frame j*W + r)."""
+        n = self.F * self.cap * 9
+        self.send[:n].copy_(det.reshape(-1))
+        self.send[n:].copy_(ndet.view(torch.float32) if ndet.dtype == torch.int32 else ndet.int().view(torch.float32))
+        if self.world == 1:
+            self.recv.copy_(self.send)
+        else:
+            dist.all_gather_into_tensor(self.recv, self.send)
+        blocks = self.recv.view(self.world, self.row)
+        return (blocks[:, :n].reshape(self.world, self.F, self.cap, 9),
+                blocks[:, n:].contiguous().view(torch.int32))
+
+
 def gather_detections(det, ndet):
-    """det [F_local, cap, 9] f32, ndet [F_local] i32 (same F_local on every rank) ->
-    on every rank: det [W, F_local, cap, 9], ndet [W, F_local].  Frame (r, j) is global frame j*W + r."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return det.unsqueeze(0), ndet.unsqueeze(0)
-    W = dist.get_world_size()
-    dets = [torch.empty_like(det) for _ in range(W)]
-    nds = [torch.empty_like(ndet) for _ in range(W)]
-    dist.all_gather(dets, det.contiguous())
-    dist.all_gather(nds, ndet.contiguous())
-    return torch.stack(dets, 0), torch.stack(nds, 0)
+    """One-shot form of DetectionGather (allocates; use the class on a hot path)."""
+    return DetectionGather(det.shape[0], det.shape[1], det.device)(det, ndet)
 
 
 def interleave(det_all, ndet_all):

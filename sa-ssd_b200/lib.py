@@ -34,10 +34,12 @@ class GConvDesc(ctypes.Structure):
 GCONV_TABLE, GCONV_CONV2D, GCONV_ROWS = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2
 CONV2D_TILE_H, CONV2D_TILE_W = 8, 16      # SASSD_CONV2D_TILE_H / _W of the header
+TILE_DIST_MAX = 9                         # SASSD_TILE_DIST_MAX
+SPCONV_TILE_ROWS = 128                    # SASSD_SPCONV_TILE_ROWS
 
 OK = 0
 ERRORS = {-1: "SASSD_ERR_ARG", -2: "SASSD_ERR_LAUNCH", -3: "SASSD_ERR_WORKSPACE", -4: "SASSD_ERR_UNSUPPORTED"}
-FLAGS = {1: "VOXEL_CAP", 2: "ROWS_CAP", 4: "GUIDED_CAP", 8: "NMS_CAP", 16: "HASH_FULL"}
+FLAGS = {1: "VOXEL_CAP", 2: "ROWS_CAP", 4: "GUIDED_CAP", 8: "NMS_CAP", 16: "HASH_FULL", 32: "DET_CAP"}
 
 P = c_void_p
 _SIGNATURES = {
@@ -49,28 +51,29 @@ _SIGNATURES = {
     "sassd_anchor_mask_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sassd_anchor_mask": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, c_size_t, P]),
     "sassd_hash_build": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
-    "sassd_rulebook_subm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "sassd_rulebook_subm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
     "sassd_rulebook_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_rulebook_conv_outputs": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, c_size_t, P]),
-    "sassd_rulebook_conv_nbr": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P]),
+    "sassd_rulebook_conv_nbr": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
     "sassd_rulebook_pairs": (c_int, [P, P, c_int, P, P, P]),
     "sassd_gconv": (c_int, [ctypes.POINTER(GConvDesc), P, P, P, P, P, P, P, P]),
     "sassd_gconv_pack_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_gconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "sassd_conv2d_f16x3": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P]),
-    "sassd_conv2d_f16x3_occ": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P, c_int, P, P]),
+    "sassd_conv2d_f16x3_occ": (c_int, [ctypes.POINTER(Conv2dDesc), P, P, P, P, P, P, P, c_int, P, P, P]),
     "sassd_rotate_overlap_eval": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P]),
     "sassd_kitti_match": (c_int, [c_int, P, P, P, P, P, P, P, P, P, P, P, P, c_int, ctypes.c_double, c_int, c_int, P, P,
                                   P, P]),
     "sassd_spconv_pack_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sassd_spconv_pack": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
-    "sassd_spconv_f16x3": (c_int, [ctypes.POINTER(SpconvDesc), P, P, P, P, P, P, P, P, P]),
+    "sassd_spconv_workspace_bytes": (c_size_t, []),
+    "sassd_spconv_f16x3": (c_int, [ctypes.POINTER(SpconvDesc), P, P, P, P, P, P, P, P, P, P, c_size_t, P, P]),
     "sassd_features_to_split": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "sassd_split_rows_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "sassd_sparse_to_bev_split": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "sassd_sparse_to_bev": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "sassd_decode_select_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, P, P, P, P, c_int, P,
+    "sassd_decode_select": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, c_float, P, P, P, P, c_int, P,
                                     P, c_size_t, P]),
     "sassd_pswarp": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_float, c_float, c_float, P, P]),
     "sassd_rescore_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

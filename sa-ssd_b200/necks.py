@@ -97,18 +97,18 @@ class VxNet(nn.Module):
             index = ops.hash_build(ops.HashIndex(cap, dev), coors, d_rows, x.batch_size, shape, x.status)
             x._index = index
             for lvl in range(4):
-                nbr = ops.rulebook_subm(coors, d_rows, shape, index)
+                nbr, tmask = ops.rulebook_subm(coors, d_rows, shape, index)
                 ev = torch.cuda.Event(); ev.record(side_stream)
-                x.indice_dict["subm%d" % lvl] = spconv.Rulebook(nbr, coors, d_rows, shape, index, ev)
+                x.indice_dict["subm%d" % lvl] = spconv.Rulebook(nbr, coors, d_rows, shape, index, ev, tmask)
                 if lvl == 3:
                     break
                 D, H, W = ops.conv_out_shape(shape)
                 cap = max(1, min(int(cap * x.row_cap_factor), x.batch_size * D * H * W))
-                co, dn, nbr2, so = ops.rulebook_conv(coors, d_rows, x.batch_size, shape, index, cap, x.status,
-                                                     ws_key="rbconv%d" % lvl)
+                co, dn, nbr2, so, tmask2 = ops.rulebook_conv(coors, d_rows, x.batch_size, shape, index, cap, x.status,
+                                                             ws_key="rbconv%d" % lvl)
                 index = ops.hash_build(ops.HashIndex(cap, dev), co, dn, x.batch_size, so, x.status)
                 ev = torch.cuda.Event(); ev.record(side_stream)
-                x.indice_dict["down%d" % lvl] = spconv.Rulebook(nbr2, co, dn, so, index, ev)
+                x.indice_dict["down%d" % lvl] = spconv.Rulebook(nbr2, co, dn, so, index, ev, tmask2)
                 coors, d_rows, shape = co, dn, so
         x._rulebook_stream = side_stream   # keep the stream (and its tensors) alive with the tensor
 
@@ -155,7 +155,7 @@ class BEVNet(nn.Module):
                                                   padding=k // 2, bias=False))
             setattr(self, "bn%d" % i, nn.BatchNorm2d(num_filters, eps=1e-3, momentum=0.01))
         self.num_filters = num_filters
-        self.precision = ops.PREC_FP32
+        self.precision = ops.DEFAULT_PRECISION
         self._packed = {}
 
     def _weights(self, i, dc_order):

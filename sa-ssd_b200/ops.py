@@ -18,6 +18,10 @@ from .lib import (GCONV_CONV2D, GCONV_ROWS, GCONV_TABLE, PREC_F16X3, PREC_FP32, 
                   check)
 
 NMS_CAP = 4096
+# Product default: every conv on the tcgen05 kernels with the fp32-accurate 3xFP16 operand split (csrc/spconv_split.cu,
+# csrc/conv2d_tma.cu).  PREC_FP32 (CUDA-core FFMA) and PREC_TF32X3 stay selectable per model
+# (SingleStageDetector.set_precision) for bisecting.
+DEFAULT_PRECISION = PREC_F16X3
 
 
 def _L():
@@ -150,14 +154,23 @@ def hash_build(index, coors, d_rows, batch, shape, status):
     return index
 
 
+def _tile_mask_buffer(rows_cap, device):
+    """int32 per 128-row tile: which of the 27 taps occur in the tile (written by the rulebook kernels, read by
+    spconv_split to skip absent taps)."""
+    n = (rows_cap + _lib.SPCONV_TILE_ROWS - 1) // _lib.SPCONV_TILE_ROWS
+    return torch.empty((max(n, 1),), dtype=torch.int32, device=device)
+
+
 def rulebook_subm(coors, d_rows, shape, index, nbr=None):
+    """Returns (nbr [rows_cap, 27], tile_mask [tiles])."""
     D, H, W = shape
     rows_cap = coors.shape[0]
     if nbr is None:
         nbr = torch.empty((rows_cap, 27), dtype=torch.int32, device=coors.device)
+    tmask = _tile_mask_buffer(rows_cap, coors.device)
     _call("sassd_rulebook_subm", None, _ptr(coors), _ptr(d_rows), rows_cap, D, H, W, _ptr(index.keys), _ptr(index.vals),
-                                   index.slots, _ptr(nbr), _stream())
-    return nbr
+                                   index.slots, _ptr(nbr), _ptr(tmask), _stream())
+    return nbr, tmask
 
 
 def conv_out_shape(shape):
@@ -165,7 +178,7 @@ def conv_out_shape(shape):
 
 
 def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, status, ws=None, ws_key="rbconv"):
-    """Strided (k3,s2,p1) rulebook.  Returns coors_out [cap,4], d_rows_out [1], nbr [cap,27], out_shape."""
+    """Strided (k3,s2,p1) rulebook.  Returns coors_out [cap,4], d_rows_out [1], nbr [cap,27], out_shape, tile_mask."""
     dev = coors_in.device
     D, H, W = shape
     Do, Ho, Wo = conv_out_shape(shape)
@@ -177,9 +190,10 @@ def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, sta
     _call("sassd_rulebook_conv_outputs", None, _ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
                                            _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(status), _ptr(w),
                                            w.numel(), _stream())
+    tmask = _tile_mask_buffer(rows_cap_out, dev)
     _call("sassd_rulebook_conv_nbr", None, _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, D, H, W, _ptr(index_in.keys),
-                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _stream())
-    return coors_out, d_rows_out, nbr, [Do, Ho, Wo]
+                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _ptr(tmask), _stream())
+    return coors_out, d_rows_out, nbr, [Do, Ho, Wo], tmask
 
 
 def rulebook_pairs(nbr, d_rows):
@@ -268,17 +282,20 @@ def sparse_to_bev(feat, coors, d_rows, C, D, H, W, bev):
 
 # ---------------------------------------------------------------------------- head tail
 def decode_select(head, num_class, anchors, mask, thr, k_cap, status, ws=None):
-    """head [B,H,W,stride] NHWC.  Returns boxes [B,k_cap,7], labels, index, d_k [B]."""
+    """head [B,H,W,stride] NHWC; anchors [Na,7] (shared) or [B,Na,7] (per frame).
+    Returns boxes [B,k_cap,7], labels, index, d_k [B]."""
     dev = head.device
     B, H, W, stride = head.shape
-    na = anchors.shape[0]
+    per_frame = 1 if anchors.dim() == 3 else 0
+    assert not per_frame or anchors.shape[0] == B
+    na = anchors.shape[-2]
     boxes = torch.empty((B, k_cap, 7), dtype=torch.float32, device=dev)
     labels = torch.empty((B, k_cap), dtype=torch.int32, device=dev)
     index = torch.empty((B, k_cap), dtype=torch.int32, device=dev)
     d_k = torch.empty((B,), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_decode_select_workspace_bytes(B, na)
     w = (ws or _WS).get("decode", nbytes, dev)
-    _call("sassd_decode_select", None, _ptr(head), stride, B, H, W, num_class, _ptr(anchors), _ptr(mask), na,
+    _call("sassd_decode_select", None, _ptr(head), stride, B, H, W, num_class, _ptr(anchors), per_frame, _ptr(mask), na,
                                    ctypes.c_float(thr), _ptr(boxes), _ptr(labels), _ptr(index), _ptr(d_k), k_cap,
                                    _ptr(status), _ptr(w), w.numel(), _stream())
     return boxes, labels, index, d_k
@@ -372,6 +389,7 @@ class SplitMap:
 
 
 TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # constant-region tile skipping in the BEV convs
+CONV2D_COUNTERS = None     # bench instrumentation: {label: int32[2] device tensor} += tiles computed, += tiles
 _TILE_FAR = 1 << 20
 
 
@@ -380,6 +398,21 @@ def _tile_dist(batch, H, W, device):
         return None
     th, tw = _lib.CONV2D_TILE_H, _lib.CONV2D_TILE_W
     return torch.full((batch * ((H + th - 1) // th) * ((W + tw - 1) // tw),), _TILE_FAR, dtype=torch.int32, device=device)
+
+
+def tile_skipping_valid(H, W, reach):
+    """Conditions under which the constant-region rule of sassd_conv2d_f16x3_occ is exact.  (a) tile distances are
+    only recorded up to SASSD_TILE_DIST_MAX pixels, so a layer further than that from the scattered map cannot tell
+    "far" from "just out of range".  (b) zero padding disturbs the constant up to reach-1 pixels from the image edge
+    and the kernel exempts only the outermost tile row / column: those edge tiles must be at least that deep, which
+    fails for a thin partial last tile (H % 8 or W % 16 small).  The C entry point checks the same and returns
+    SASSD_ERR_UNSUPPORTED; here the layer simply falls back to computing every tile."""
+    th, tw = _lib.CONV2D_TILE_H, _lib.CONV2D_TILE_W
+    if reach > _lib.TILE_DIST_MAX:
+        return False
+    last_h = H - (H - 1) // th * th
+    last_w = W - (W - 1) // tw * tw
+    return min(last_h, last_w, th, tw) >= reach - 1
 
 
 _CONV_CONSTS = {}
@@ -438,9 +471,13 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     reach, cvec = 0, None
     if dist is not None:
         reach = x.reach + (1 if taps == 9 else 0)
+        if not tile_skipping_valid(H, W, reach):
+            dist = None        # the map is computed in full from here on (see tile_skipping_valid)
+    if dist is not None:
         cvec = conv_constant(x.const, cin, weight, scale, shift, relu, cout)
     _call("sassd_conv2d_f16x3_occ", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
-          _ptr(osp), _ptr(dist), reach, _ptr(cvec), _stream())
+          _ptr(osp), _ptr(dist), reach, _ptr(cvec), _ptr(CONV2D_COUNTERS.get(label) if CONV2D_COUNTERS else None),
+          _stream())
     return (SplitMap(osp, cout, dist, reach, cvec) if osp is not None else None), of
 
 
@@ -459,7 +496,13 @@ def split_rows_float(planes, channels):
     return (planes[0].float() + planes[1].float() * (1.0 / 2048.0))[:, :channels].contiguous()
 
 
-def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d_rows=None, want_f32=False):
+SPCONV_COUNTERS = None     # bench instrumentation: int32[2] device tensor -> += executed (tile, chunk) pairs, += tiles
+SPCONV_TAP_SKIP = os.environ.get("SASSD_SPS_SKIP", "1") != "0"      # use the rulebook's tile masks
+SPCONV_TAP_SPLIT = os.environ.get("SASSD_SPS_SPLIT", "1") != "0"    # cluster tap split for layers with few tiles
+
+
+def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d_rows=None, want_f32=False,
+                 tile_mask=None, ws=None):
     """planes [2, in_cap, cin_stored] fp16; weight [taps, cin, cout] fp32 (packed on first use).
     Returns (out planes [2, rows_cap, out_ch], fp32 rows or None)."""
     taps = weight.shape[0]
@@ -474,8 +517,12 @@ def spconv_split(planes, weight, scale, shift, relu, cout, rows_cap, nbr=None, d
         d.out_f32_stride = (cout + 3) // 4 * 4
         of = torch.empty((rows_cap, d.out_f32_stride), dtype=torch.float32, device=planes.device)
     label = "spconv_split[taps=%d %d->%d]" % (taps, weight.shape[1], cout)
+    w = None
+    if SPCONV_TAP_SPLIT and taps > 1:
+        w = (ws or _WS).get("spconv_split", _L().sassd_spconv_workspace_bytes(), planes.device)
     _call("sassd_spconv_f16x3", label, ctypes.byref(d), _ptr(planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(nbr),
-          _ptr(d_rows), _ptr(out), _ptr(of), _stream())
+          _ptr(tile_mask if SPCONV_TAP_SKIP else None), _ptr(d_rows), _ptr(out), _ptr(of), _ptr(w),
+          0 if w is None else w.numel(), _ptr(SPCONV_COUNTERS), _stream())
     return out, of
 
 

@@ -138,27 +138,29 @@ def kitti_bbox2results(boxes_lidar, scores, labels, meta, class_names=None):
     alphas = -np.arctan2(-boxes_lidar[:, 1], boxes_lidar[:, 0]) \
         + boxes_lidar[:, 6]
 
-    rows = {k: [] for k in _RESULT_KEYS}
-    rows['image_idx'] = []
-    for lb, score, cam, rect, alpha in zip(labels, scores, boxes_cam, box2d,
-                                           alphas):
-        if rect[0] > img_w or rect[1] > img_h or rect[2] < 0 or rect[3] < 0:
-            continue
-        rect[2:] = np.minimum(rect[2:], [img_w, img_h])
-        rect[:2] = np.maximum(rect[:2], [0, 0])
-        rows['name'].append(class_names[lb])
-        rows['truncated'].append(0.0)
-        rows['occluded'].append(0)
-        rows['alpha'].append(alpha)
-        rows['bbox'].append(rect)
-        rows['dimensions'].append(cam[[3, 4, 5]])
-        rows['location'].append(cam[:3])
-        rows['rotation_y'].append(cam[6])
-        rows['score'].append(score)
-        rows['image_idx'].append(int(sample_id))
-    if not rows['name']:
+    # one mask instead of the reference's per-box loop (transforms.py:252-271): drop boxes whose projection lies
+    # wholly outside the image, clip the rest to it
+    labels = np.asarray(labels)
+    keep = ~((box2d[:, 0] > img_w) | (box2d[:, 1] > img_h) | (box2d[:, 2] < 0) | (box2d[:, 3] < 0))
+    n = int(keep.sum())
+    if n == 0:
         return empty_result_anno()
-    return {k: np.stack(v) for k, v in rows.items()}
+    rect = box2d[keep]
+    rect[:, 2:] = np.minimum(rect[:, 2:], [img_w, img_h])
+    rect[:, :2] = np.maximum(rect[:, :2], [0, 0])
+    cam = boxes_cam[keep]
+    names = np.asarray(class_names)[labels[keep]]
+    names = names.astype('<U%d' % int(np.char.str_len(names).max()))     # dtype np.stack gives a list of str
+    return {
+        'name': names, 'truncated': np.zeros(n), 'occluded': np.zeros(n, np.int64), 'alpha': alphas[keep],
+        'bbox': rect, 'dimensions': cam[:, 3:6], 'location': cam[:, :3], 'rotation_y': cam[:, 6],
+        'score': np.asarray(scores)[keep], 'image_idx': np.full(n, int(sample_id), np.int64),
+    }
+
+
+def kitti_bbox2results_batch(boxes_lidar, scores, labels, metas, class_names=None):
+    """All frames of a batch (the loop of single_stage.py:127-131 over ``kitti_bbox2results``)."""
+    return [kitti_bbox2results(b, s, l, m, class_names) for b, s, l, m in zip(boxes_lidar, scores, labels, metas)]
 
 
 _LINE_DEFAULTS = (('name', None), ('truncated', -1), ('occluded', -1), ('alpha', -10), ('bbox', None),

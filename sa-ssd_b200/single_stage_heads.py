@@ -44,7 +44,7 @@ class SSDRotateHead(nn.Module):
         self.conv_cls = nn.Conv2d(num_output_filters, num_anchor_per_loc * num_class, 1)
         self.conv_box = nn.Conv2d(num_output_filters, num_anchor_per_loc * box_code_size, 1)
         self.conv_dir_cls = nn.Conv2d(num_output_filters, num_anchor_per_loc * 2, 1)
-        self.precision = ops.PREC_FP32
+        self.precision = ops.DEFAULT_PRECISION
         self._packed = None
         self.k_cap = 8192   # guided anchors kept per frame (overflow raises SASSD_FLAG_GUIDED_CAP)
 
@@ -96,8 +96,8 @@ class SSDRotateHead(nn.Module):
 
     def guided_anchors_device(self, head, anchors, anchors_mask, thr, status):
         """No-sync path: head map -> (boxes [B,k_cap,7], labels, anchor index, d_k [B])."""
-        a = anchors[0] if anchors.dim() == 3 else anchors
-        return ops.decode_select(head, self._num_class, a.contiguous().float(),
+        # [Na,7] = one table for the batch (fused path); [B,Na,7] = per-frame tables (reference signature)
+        return ops.decode_select(head, self._num_class, anchors.contiguous().float(),
                                  anchors_mask.to(torch.uint8).contiguous(), float(thr), self.k_cap, status)
 
     def get_guided_anchors(self, box_preds, cls_preds, dir_cls_preds, anchors, anchors_mask, gt_bboxes, gt_labels,
@@ -178,7 +178,7 @@ class PSWarpHead(nn.Module):
             nn.ReLU(inplace=True),
             nn.Conv2d(out_channels, out_channels, 1, 1, padding=0, bias=False),
         )
-        self.precision = ops.PREC_FP32
+        self.precision = ops.DEFAULT_PRECISION
         self._packed = None
         self.det_cap = 512
 

@@ -22,8 +22,9 @@ SPLIT_ROWS = True   # F16X3 sparse layers keep their features as split fp16 rows
 class Rulebook:
     """nbr [rows_cap, 27] + the output coordinate set of one indice_key."""
 
-    def __init__(self, nbr, coors_out, d_rows_out, shape_out, index_out=None, event=None):
+    def __init__(self, nbr, coors_out, d_rows_out, shape_out, index_out=None, event=None, tile_mask=None):
         self.nbr, self.coors_out, self.d_rows_out, self.shape_out = nbr, coors_out, d_rows_out, shape_out
+        self.tile_mask = tile_mask   # int32 per 128-row output tile: taps that occur in the tile (tap skipping)
         self.index_out = index_out   # hash index over coors_out when it was prebuilt
         self.event = event           # recorded on the stream that built the rulebook (None = same stream)
 
@@ -134,7 +135,7 @@ class _SparseConvBase(nn.Module):
         bound = 1.0 / (in_channels * ks[0] * ks[1] * ks[2]) ** 0.5
         nn.init.uniform_(self.weight, -bound, bound)
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
-        self.precision = ops.PREC_FP32
+        self.precision = ops.DEFAULT_PRECISION
         if not (ks in ((3, 3, 3), (1, 1, 1))):
             raise NotImplementedError("kernel sizes used by SA-SSD: 3x3x3 and 1x1x1")
         if ks == (3, 3, 3) and not subm and (st != (2, 2, 2) or pd != (1, 1, 1)):
@@ -148,14 +149,14 @@ class _SparseConvBase(nn.Module):
                 torch.cuda.current_stream().wait_event(rb.event)
             return rb
         if self.subm:
-            nbr = ops.rulebook_subm(x._indices, x.d_rows, x.spatial_shape, x.hash_index())
-            rb = Rulebook(nbr, x._indices, x.d_rows, x.spatial_shape)
+            nbr, tmask = ops.rulebook_subm(x._indices, x.d_rows, x.spatial_shape, x.hash_index())
+            rb = Rulebook(nbr, x._indices, x.d_rows, x.spatial_shape, tile_mask=tmask)
         else:
             D, H, W = ops.conv_out_shape(x.spatial_shape)
             cap = min(int(x.rows_cap * x.row_cap_factor), x.batch_size * D * H * W)
-            co, dn, nbr, so = ops.rulebook_conv(x._indices, x.d_rows, x.batch_size, x.spatial_shape, x.hash_index(),
-                                                max(cap, 1), x.status)
-            rb = Rulebook(nbr, co, dn, so)
+            co, dn, nbr, so, tmask = ops.rulebook_conv(x._indices, x.d_rows, x.batch_size, x.spatial_shape,
+                                                       x.hash_index(), max(cap, 1), x.status)
+            rb = Rulebook(nbr, co, dn, so, tile_mask=tmask)
         if key is not None:
             x.indice_dict[key] = rb
         return rb
@@ -175,7 +176,7 @@ class _SparseConvBase(nn.Module):
                 return x._derive(None, split=out, channels=self.out_channels)
             rb = self._rulebook(x)
             out, _ = ops.spconv_split(planes, wp, scale, shift, relu, self.out_channels, rb.nbr.shape[0], nbr=rb.nbr,
-                                      d_rows=rb.d_rows_out)
+                                      d_rows=rb.d_rows_out, tile_mask=rb.tile_mask)
             if self.subm:
                 return x._derive(None, split=out, channels=self.out_channels)
             return x._derive(None, indices=rb.coors_out, spatial_shape=rb.shape_out, d_rows=rb.d_rows_out,

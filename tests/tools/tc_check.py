@@ -168,18 +168,38 @@ if stage in ("tmafull",):
     run_tma(1, 200, 176, 256, 128, 9, True, "tma full 256->128")
 
 
-def run_split(M, cin, cout, taps, relu, tag, density=0.3):
+def tile_masks(nb, n_rows):
+    """What the rulebook kernels record: per 128-row tile, the taps that occur among its first n_rows rows."""
+    M, taps = nb.shape
+    nt = (M + 127) // 128
+    pad = np.full((nt * 128, taps), -1, np.int64)
+    pad[:n_rows] = nb[:n_rows]
+    present = (pad.reshape(nt, 128, taps) >= 0).any(1)
+    return (present * (1 << np.arange(taps))[None, :]).sum(1).astype(np.int32)
+
+
+def run_split(M, cin, cout, taps, relu, tag, density=0.3, masks=False, absent=0.0):
+    """masks: pass the per-tile tap masks (tap skipping); absent: fraction of (tile, tap) combinations with no
+    neighbour at all, so that whole chunks really are skipped."""
     rs = np.random.RandomState(cin * 100 + cout)
     x = torch.randn(M, cin, device=dev)
     w = torch.randn(taps, cin, cout, device=dev) * 0.1
     scale = torch.rand(cout, device=dev) + 0.5
     shift = torch.randn(cout, device=dev) * 0.1
-    nbr = None
+    nbr = tm = None
     if taps > 1:
-        nbr = torch.from_numpy(np.where(rs.rand(M, taps) < density, rs.randint(0, M, (M, taps)), -1).astype(np.int32)).to(dev)
+        nb = np.where(rs.rand(M, taps) < density, rs.randint(0, M, (M, taps)), -1).astype(np.int32)
+        if absent > 0:
+            gone = rs.rand((M + 127) // 128, taps) < absent
+            gone[0, :] = True        # a tile with no pair at all must still produce act(shift)
+            nb[np.repeat(gone, 128, axis=0)[:M]] = -1
+        nbr = torch.from_numpy(nb).to(dev)
+        if masks:
+            tm = torch.from_numpy(tile_masks(nb, M - 5)).to(dev)
     d_rows = torch.tensor([M - 5], dtype=torch.int32, device=dev)
     planes = ops.features_to_split(x)
-    out, of = ops.spconv_split(planes, w, scale, shift, relu, cout, M, nbr=nbr, d_rows=d_rows, want_f32=True)
+    out, of = ops.spconv_split(planes, w, scale, shift, relu, cout, M, nbr=nbr, d_rows=d_rows, want_f32=True,
+                               tile_mask=tm)
     torch.cuda.synchronize()
     xd, wd = x.double().cpu(), w.double().cpu()
     ref = torch.zeros(M, cout, dtype=torch.float64)
@@ -216,6 +236,15 @@ if stage in ("split",):
     run_split(3000, 64, 64, 27, True, "split table 64->64")
     run_split(20000, 64, 64, 27, True, "split table 64->64 big")
     run_split(3000, 64, 64, 1, True, "split rows 64->64")
+    # tap skipping (tile masks) with whole (tile, tap) combinations absent; <= 74 tiles also take the cluster tap split
+    run_split(300, 4, 16, 27, True, "skip 4->16", masks=True, absent=0.5)
+    run_split(3000, 16, 32, 27, True, "skip 16->32", masks=True, absent=0.5)
+    run_split(3000, 32, 32, 27, True, "skip 32->32", masks=True, absent=0.4)
+    run_split(3000, 64, 64, 27, True, "skip 64->64 (tap split)", masks=True, absent=0.4)
+    run_split(9400, 64, 64, 27, True, "skip 64->64 74 tiles", masks=True, absent=0.4)
+    run_split(9500, 64, 64, 27, True, "skip 64->64 75 tiles", masks=True, absent=0.4)
+    run_split(20000, 64, 64, 27, True, "skip 64->64 big", masks=True, absent=0.4)
+    run_split(20000, 64, 64, 27, True, "skip 64->64 big sparse", masks=True, absent=0.9, density=0.5)
     print("done split")
 if stage in ("splitperf",):
     M, cin, cout, taps = 120000, 64, 64, 27
@@ -227,16 +256,56 @@ if stage in ("splitperf",):
     nbr = torch.from_numpy(nb).to(dev)
     d_rows = torch.tensor([M], dtype=torch.int32, device=dev)
     planes = ops.features_to_split(x)
-    for _ in range(2):
-        ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr, d_rows=d_rows)
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr, d_rows=d_rows)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
     P = int((nb >= 0).sum())
-    print("splitperf dbg=%s: %.3f ms  pair-model %.0f GB/s  (%.0f clk/chunk/tile)" % (
-        os.environ.get("SASSD_SPS_DBG", "0"), ms, P * (4 * cin + 4 * cout + 8) / ms / 1e6,
-        ms * 1e-3 * 1.9e9 / (27 * (M / 128) / 148)), flush=True)
+
+    def timed(tag, nbr_t, tm, n_chunks):
+        for _ in range(2):
+            ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr_t, d_rows=d_rows, tile_mask=tm)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.spconv_split(planes, w, None, None, True, cout, M, nbr=nbr_t, d_rows=d_rows, tile_mask=tm)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        pairs = int((nbr_t.cpu().numpy() >= 0).sum())
+        print("splitperf %s dbg=%s: %.3f ms  pair-model %.0f GB/s  (%.0f clk per executed chunk)" % (
+            tag, os.environ.get("SASSD_SPS_DBG", "0"), ms, pairs * (4 * cin + 4 * cout + 8) / ms / 1e6,
+            ms * 1e-3 * 1.9e9 / (n_chunks / 148)), flush=True)
+
+    timed("all taps", nbr, None, 27 * (M / 128))
+    # 30 % of the (tile, tap) combinations absent, like the level-2 SubM rulebook of a KITTI-shaped cloud
+    nb2 = nb.copy()
+    gone = rs.rand((M + 127) // 128, taps) < 0.3
+    nb2[np.repeat(gone, 128, axis=0)[:M]] = -1
+    tm = tile_masks(nb2, M)
+    timed("30% tile-taps absent, masks", torch.from_numpy(nb2).to(dev), torch.from_numpy(tm).to(dev),
+          float(sum(bin(int(v) & 0x7ffffff).count("1") for v in tm)))
+    timed("30% tile-taps absent, no masks", torch.from_numpy(nb2).to(dev), None, 27 * (M / 128))
+    # one-frame layer sizes: 7 500 rows (59 tiles, tap split) and 14 000 rows (110 tiles)
+    for rows in (5300, 7500, 14000):
+        sub = torch.from_numpy(np.where(nb[:rows] >= rows, -1, nb[:rows])).to(dev)
+        d_rows = torch.tensor([rows], dtype=torch.int32, device=dev)
+        M_full, M = M, rows
+        timed("%d rows" % rows, sub, torch.from_numpy(tile_masks(sub.cpu().numpy(), rows)).to(dev), 27 * (rows / 128))
+        M = M_full
+        d_rows = torch.tensor([M], dtype=torch.int32, device=dev)
+
+if stage in ("splittrace",):
+    # SASSD_SPS_TRACE=2 python tests/tools/tc_check.py splittrace <rows>: per-CTA clock sums of the second launch
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 120000
+    cin = cout = 64
+    rs = np.random.RandomState(1)
+    x = torch.randn(rows, cin, device=dev)
+    w = torch.randn(27, cin, cout, device=dev) * 0.1
+    nb = np.where(rs.rand(rows, 27) < 0.35, np.clip(np.arange(rows)[:, None] + rs.randint(-300, 300, (rows, 27)), 0, rows - 1), -1).astype(np.int32)
+    gone = rs.rand((rows + 127) // 128, 27) < 0.3
+    nb[np.repeat(gone, 128, axis=0)[:rows]] = -1
+    nbr = torch.from_numpy(nb).to(dev)
+    tm = torch.from_numpy(tile_masks(nb, rows)).to(dev)
+    d_rows = torch.tensor([rows], dtype=torch.int32, device=dev)
+    planes = ops.features_to_split(x)
+    for _ in range(3):
+        ops.spconv_split(planes, w, None, None, True, cout, rows, nbr=nbr, d_rows=d_rows, tile_mask=tm)
+    torch.cuda.synchronize()
+    print("splittrace done", rows)
