@@ -173,6 +173,9 @@ typedef struct {
     int32_t cin, cin_stored;       /* valid / stored input channels */
     int32_t cout, taps, relu;
     int32_t out_f32_stride, out_split_ch;
+    int32_t tile_order;            /* sassd_conv2d_f16x3_occ: 0 = tiles round-robin over the CTAs (best with several steps
+                                      in flight), 1 = computed tiles first, constant tiles after (best for one step at a
+                                      time: no CTA gets two computed tiles while others only store constants) */
 } sassd_conv2d_desc;
 int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
                        const float* shift, float* out_f32, void* out_split, sassd_stream_t stream);

@@ -20,6 +20,9 @@
 
 #include <cstdlib>
 
+#include <cstdio>
+#include <vector>
+
 #include "tc_common.cuh"
 
 namespace tma {
@@ -77,6 +80,7 @@ struct Conv2dArgs {
     const float* cvec;    // output constant of the tiles that see a constant input (tile_dist > reach, not on the border)
     int reach;
     int* counters;        // optional [2]: += tiles computed (not stored as a constant), += tiles (bench instrumentation)
+    long long* trace;     // optional [grid][8] clock64 sums per CTA (SASSD_TMA_TRACE=n: n-th launch, timing experiments)
     int tile_order;       // 1: computed tiles first (SASSD_TMA_ORDER=1), 0: round-robin
     int dbg;              // SASSD_TMA_DBG (timing experiments only): 1 = reuse stale B stages, 2 = reuse stale A stages,
                           // 4 = plain MMAs (no operand collector)
@@ -317,32 +321,44 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         int computed = 0;
+        long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+        long long t_acc = 0, t_full = 0, t_iss = 0;
+        const long long t_begin = tr ? clock64() : 0;
         for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
             const int tile = tile_at(k);
             if (tile_is_constant(p, tile, (tile / tiles_x) % tiles_y, tile % tiles_x, tiles_y, tiles_x)) continue;
             ++computed;
+            long long c0 = tr ? clock64() : 0;
             mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
             tc_fence_after();
+            if (tr) t_acc += clock64() - c0;
             const uint32_t d_big = tmem_base + (uint32_t)(acc * 2 * BN), d_small = d_big + (uint32_t)BN;
             uint32_t first = 0u;
             for (int ch = 0; ch < nchunks; ++ch) {
+                c0 = tr ? clock64() : 0;
                 mbar_wait(full(stage), phase);
                 tc_fence_after();
+                const long long c1 = tr ? clock64() : 0;
                 const uint32_t ah = lo0 + (uint32_t)stage * kStageLo, al = ah + kATileLo;
                 const uint32_t bh = al + kATileLo, bl = bh + kBTileLo;
                 if (leader) {
                     // Each K=16 step reads one operand once for two of its three products: bh through the
                     // weight-stationary form's B collector when N = 256 (B is the larger operand), ah through the A
                     // collector otherwise.
+                    if (BN == 256 && !(p.dbg & 4)) {
 #pragma unroll
-                    for (uint32_t k16 = 0; k16 < 4; ++k16) {
-                        const uint32_t ko = k16 * kDescK16;
-                        const uint32_t f = k16 ? 1u : first;
-                        if constexpr (BN == 256) {
+                        for (uint32_t k16 = 0; k16 < 4; ++k16) {
+                            const uint32_t ko = k16 * kDescK16;
+                            const uint32_t f = k16 ? 1u : first;
                             mma_f16_ws_lo<1>(d_big, ah + ko, bh + ko, idesc, f);
                             mma_f16_ws_lo<2>(d_small, al + ko, bh + ko, idesc, f);
                             mma_f16_ws_lo<0>(d_small, ah + ko, bl + ko, idesc, 1u);
-                        } else {
+                        }
+                    } else {
+#pragma unroll
+                        for (uint32_t k16 = 0; k16 < 4; ++k16) {
+                            const uint32_t ko = k16 * kDescK16;
+                            const uint32_t f = k16 ? 1u : first;
                             mma_f16_lo(d_small, al + ko, bh + ko, idesc, f);
                             mma_f16_acoll_lo<1>(d_big, ah + ko, bh + ko, idesc, f);
                             mma_f16_acoll_lo<2>(d_small, ah + ko, bl + ko, idesc, 1u);
@@ -351,6 +367,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                     mma_commit(empty(stage));
                 }
                 __syncwarp();
+                if (tr) { t_full += c1 - c0; t_iss += clock64() - c1; }
                 first = 1u;
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -358,6 +375,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             __syncwarp();
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
+        if (tr && leader) { tr[0] = t_acc; tr[1] = t_full; tr[2] = t_iss; tr[3] = clock64() - t_begin; tr[4] = computed; }
         if (p.counters && leader) {
             if (computed) atomicAdd(&p.counters[0], computed);
             if (blockIdx.x == 0) atomicAdd(&p.counters[1], ntiles);
@@ -367,6 +385,8 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         uint32_t acc_phase = 0;
         uint32_t store_it = 0;
         const uint32_t my_stage = ostage_base + (uint32_t)warp * 8192u;
+        long long* tr = (p.trace && threadIdx.x == 0) ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+        long long e_wait = 0, e_drain = 0;
         for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
             const int tile = tile_at(k);
             const int b = tile / (tiles_y * tiles_x);
@@ -375,14 +395,18 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 drain_tile<BN>(p, &omap, 0u, warp, lane, b, ty, tx, true, my_stage, store_it, [] {}, true);
                 continue;
             }
+            const long long c0 = tr ? clock64() : 0;
             if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
             __syncwarp();
             tc_fence_after();
+            const long long c1 = tr ? clock64() : 0;
             const uint32_t bar = tmem_empty(acc);
             drain_tile<BN>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), warp, lane, b, ty, tx, true, my_stage, store_it,
                            [bar] { mbar_arrive(bar); });
+            if (tr) { e_wait += c1 - c0; e_drain += clock64() - c1; }
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
+        if (tr) { tr[5] = e_wait; tr[6] = e_drain; }
         if (lane == 0) bulk_wait_group_all();
         __syncwarp();
     }
@@ -696,8 +720,19 @@ extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in
     a.batch = d->batch; a.H = d->H; a.W = d->W; a.cin = d->cin; a.cout = d->cout; a.taps = d->taps; a.relu = d->relu;
     a.out_f32_stride = d->out_f32_stride; a.out_split_ch = d->out_split_ch;
     a.tile_dist = tile_dist; a.reach = reach; a.cvec = const_out; a.counters = counters;
-    static const int tile_order = [] { const char* e = getenv("SASSD_TMA_ORDER"); return e ? atoi(e) : 0; }();
-    a.tile_order = tile_order;
+    a.trace = nullptr;
+    static const int trace_call = [] { const char* e = getenv("SASSD_TMA_TRACE"); return e ? atoi(e) : 0; }();
+    static long long* trace_buf = nullptr;
+    static int trace_calls = 0;
+    bool tracing = false;
+    if (trace_call && d->cout == 256 && d->taps == 9 && ++trace_calls == trace_call) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 148 * 8 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 148 * 8 * sizeof(long long), (cudaStream_t)stream_);
+        a.trace = trace_buf;
+        tracing = true;
+    }
+    static const int tile_order_env = [] { const char* e = getenv("SASSD_TMA_ORDER"); return e ? atoi(e) : -1; }();
+    a.tile_order = tile_order_env >= 0 ? tile_order_env : d->tile_order;      // the environment overrides (experiments)
     static const int dbg = [] { const char* e = getenv("SASSD_TMA_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -718,7 +753,20 @@ extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in
     if (d->cout <= 128) return launch2<128>(map, omap, a, stream);
     // opt-in: measured equal to the single-CTA kernel (both sit at the chip's sustained tensor rate)
     static const bool use_pair = [] { const char* e = getenv("SASSD_TMA_PAIR"); return e && atoi(e) != 0; }();
-    if (!use_pair) return launch2<256>(map, omap, a, stream);
+    if (!use_pair) {
+        const int rc = launch2<256>(map, omap, a, stream);
+        if (tracing) {       // timing experiment: per-CTA clock sums of this launch -> stderr
+            std::vector<long long> h(148 * 8);
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "TMA_TRACE B=%d: cta | mma: wait_acc wait_full issue total tiles | epi(warp0): wait_full drain\n", d->batch);
+            for (int c = 0; c < 148; c += (c < 3 ? 1 : 48)) {
+                const long long* q = &h[(size_t)c * 8];
+                fprintf(stderr, "TMA_TRACE %3d | %8lld %8lld %8lld %8lld %3lld | %8lld %8lld\n", c, q[0], q[1], q[2], q[3], q[4], q[5], q[6]);
+            }
+        }
+        return rc;
+    }
     // weight pack as a 2-D tensor of 128-byte rows (already in UMMA swizzled order: no TMA swizzle)
     const int kchunks = sassd_div_up(d->cin, BKC);
     CUtensorMap bmap;

@@ -52,6 +52,9 @@ struct Cfg3 {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {   // arrive when this thread's prior cp.async land
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -119,9 +122,7 @@ struct ChunkSet {
     }
 };
 
-// CS = stored input channels per tap (8 / 16 / 32 / 64) as a compile-time constant for the layers of the network - the
-// producers' piece / tap arithmetic then folds to shifts - or 0 for any other width (run-time arithmetic).
-template <int TABLE, int BN, int CS>
+template <int TABLE, int BN>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) spconv_split_kernel(const Args p) {
     using C = Cfg3<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -130,7 +131,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
     const uint32_t nbr_base = base + C::STAGES * C::STAGE_BYTES;
     const int* nbr_smem = (const int*)(base_ptr + C::STAGES * C::STAGE_BYTES);
     const uint32_t bar_base = nbr_base + 2 * C::NBR_TILE_BYTES;
-    auto full_a = [&](int s) { return bar_base + 8u * s; };                       // 256 async producer arrivals
+    auto full_a = [&](int s, int w) { return bar_base + 512u + 8u * (s * PROD_WARPS + w); };   // one per producer warp:
+                                                                   // 32 async arrivals each, on separate words
     auto full_b = [&](int s) { return bar_base + 8u * (C::STAGES + s); };         // weight block landed
     auto ready_a = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };    // full_a + proxy fence done
     auto empty = [&](int s) { return bar_base + 8u * (3 * C::STAGES + s); };
@@ -138,7 +140,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
     auto tmem_empty = [&](int a) { return bar_base + 8u * (4 * C::STAGES + 2 + a); };
     auto nbr_full = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 4 + b); };
     auto nbr_empty = [&](int b) { return bar_base + 8u * (4 * C::STAGES + 6 + b); };
-    const uint32_t peer_done = bar_base + 8u * (4 * C::STAGES + 8);               // leader: peer's partial sums are in L2
+    const uint32_t peer_done = bar_base + 8u * (4 * C::STAGES + 8);               // the peer's partial sums of my rows are in L2
     const uint32_t tmem_slot = bar_base + 8u * (4 * C::STAGES + 9);
     volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(base_ptr + (tmem_slot - base));
 
@@ -150,7 +152,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
     // Tap packing: a chunk is 64 K-columns = `tpg` taps of `cin` stored channels each (cin 8/16/32 -> 8/4/2 taps per
     // chunk), so the narrow early layers run 4/7/14 chunks per tile instead of 27.  The weight pack has the same
     // K order (sassd_spconv_pack).
-    const int cin = CS ? CS : p.cin;
+    const int cin = p.cin;
     const int ppt = cin >> 3;                                // 16-byte pieces per tap
     const int tpg = (BKC % cin == 0) ? BKC / cin : 1;        // taps per chunk
     const int nchunks = (p.taps + tpg - 1) / tpg;
@@ -159,14 +161,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(full_a(s), PROD_WARPS * 32);
+            for (int w = 0; w < PROD_WARPS; ++w) mbar_init(full_a(s, w), 32);
             mbar_init(full_b(s), 1);
             mbar_init(ready_a(s), 1);
             mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS); }
         for (int b = 0; b < 2; ++b) { mbar_init(nbr_full(b), 1); mbar_init(nbr_empty(b), PROD_WARPS); }
-        mbar_init(peer_done, EPI_WARPS * 32);
+        mbar_init(peer_done, (EPI_WARPS / 2) * 32);      // the peer's two giver warps
         fence_barrier_init();
     }
     if (warp == W_MMA) {
@@ -200,83 +202,84 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         }
         return ChunkSet(tm, tpg, nchunks, part, nparts).mask;
     };
+    // Every CTA streams the same weight chunks.  If they all walked the taps in the same order they would ask the
+    // same few L2 lines for the same 16 KB at the same time; each tile therefore starts at a different tap
+    // (rotation by a tile-dependent offset, identical in all roles; the sum over taps is order-independent up to fp32
+    // rounding and deterministic per tile).
+    auto rot_of = [&](int tile) { return (p.dbg & 4) ? 0 : (int)(((unsigned)tile * 11u) % (unsigned)nchunks); };
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ===================== A producers: cp.async gather of split rows =====================
-        // Nothing in this instruction stream waits for data: every thread issues its eight 16-byte copies and an
-        // asynchronous mbarrier arrive that fires when they have landed, so the gather runs STAGES chunks ahead.
-        const int pt = threadIdx.x - EPI_WARPS * 32;
-        const int r = pt & 127, hf = pt >> 7;
-        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-        const uint32_t sw = (uint32_t)(r & 7);
+        // Nothing in this instruction stream waits for data: every thread issues its eight 16-byte copies (hardware
+        // zero fill for a missing neighbour) and an asynchronous mbarrier arrive that fires when they have landed, so
+        // the gather runs STAGES chunks ahead.
+        // Lane mapping (round 2, tests/tools/ldgsts_probe.cu): the 8 lanes of an octet copy the 8 pieces of ONE
+        // 128-byte row, so an LDGSTS instruction touches 4 rows = 4 cache lines and costs ~7 clk whatever the rows hold
+        // (463 clk per 32 KB chunk).  With lane = row (round 1) an instruction touched 32 lines and the L1 serves about
+        // one line per clock: 725 clk per chunk at 35 % neighbour density, 2044 clk at 100 %.  Skipping absent rows
+        // (votes, dirty bits, ballot compaction) was measured too: the extra instructions cost more than they save.
+        const int pw = warp - EPI_WARPS;                    // rows 16 pw .. 16 pw + 15
+        const int piece = lane & 7, oct = lane >> 3;
+        const int tl = piece / ppt, pc8 = (piece - tl * ppt) * 8;     // my tap within the chunk, element offset in it
+        uint32_t offs[4];                                   // shared-memory offset of my 16 bytes of row j (any stage)
+        int rowt[4];                                        // (row j) * taps
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = pw * 16 + j * 4 + oct;
+            offs[j] = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (((uint32_t)piece ^ (uint32_t)(r & 7)) << 4);
+            rowt[j] = r * p.taps;
+        }
+        const __half* in_hi = p.in + pc8;
+        const __half* in_lo = in_hi + p.in_plane;
         int stage = 0;
         uint32_t phase = 0;
         int nb = 0;                    // neighbour-table buffer of this tile
         uint32_t nb_phase = 0;
         long long tw = 0, ti = 0, tn = 0;
-        const bool trp = tr && pt == 0;
+        const bool trp = tr && pw == 0 && lane == 0;
         for (int tile = tile0; tile < ntiles; tile += tstep) {
-            const int m = tile * BM + r;
             // rows of the table the loader thread copied for this tile (whole 16-byte units only)
             const int rows_here = min(BM, p.rows_cap - tile * BM);
             const int rows_copied = nbr_tiles ? ((rows_here * p.taps * 4) & ~15) / (p.taps * 4) : 0;
-            const int* nrow = nbr_smem + nb * (C::NBR_TILE_BYTES / 4) + r * p.taps;
-            const bool from_smem = nbr_tiles && r < rows_copied;
+            const int* ntile = nbr_smem + nb * (C::NBR_TILE_BYTES / 4);
             const uint32_t cmask = chunks_of(tile);
+            const int m0 = tile * BM + pw * 16 + oct;       // global row of j = 0
             long long c0 = trp ? clock64() : 0;
             if (nbr_tiles) {
                 if (lane == 0) mbar_wait(nbr_full(nb), nb_phase);
                 __syncwarp();
             }
             if (trp) tn += clock64() - c0;
-            for (int g = 0; g < nchunks; ++g) {
+            const int rot = rot_of(tile);
+            for (int gi = 0; gi < nchunks; ++gi) {
+                const int g = gi + rot < nchunks ? gi + rot : gi + rot - nchunks;
                 if (!((cmask >> g) & 1u)) continue;
-                // one lane polls the mbarrier, the warp follows (256 threads spinning on one shared-memory
-                // word slow every other barrier operation of the CTA)
+                // the four neighbour indices of this chunk before the wait (they do not depend on the stage)
+                const int t = g * tpg + tl;
+                const bool tap_ok = tl < tpg && t < p.taps && !(p.dbg & 32);
+                int srcs[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + 4 * j;
+                    srcs[j] = -1;
+                    if (tap_ok && m < M)
+                        srcs[j] = TABLE ? ((nbr_tiles && pw * 16 + j * 4 + oct < rows_copied) ? ntile[rowt[j] + t]
+                                                                                           : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
+                }
+                // one lane polls the mbarrier, the warp follows
                 c0 = trp ? clock64() : 0;
                 if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
                 __syncwarp();
                 const long long c1 = trp ? clock64() : 0;
-                const uint32_t a_hi = base + stage * C::STAGE_BYTES + row_off, a_lo = a_hi + A_TILE_BYTES;
-                if (!(p.dbg & 32)) {
-                    // This thread owns pieces q = 4*hf .. 4*hf+3 (8 K-columns each) of row r: piece -> (tap within the
-                    // chunk, piece within the tap) is compile-time for CS = 64 / 32 / 16 / 8.
-                    auto row_of = [&](int t) -> int {
-                        if (m >= M || t >= p.taps) return -1;
-                        return TABLE ? (from_smem ? nrow[t] : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
-                    };
-                    auto copy = [&](int q, int src, int piece) {
-                        const uint32_t nbytes = src >= 0 ? 16u : 0u;     // 0 -> hardware zero fill
-                        const __half* sp = p.in + (size_t)(src < 0 ? 0 : src) * cin + (nbytes ? piece * 8 : 0);
-                        const uint32_t off = ((uint32_t)q ^ sw) << 4;
-                        cp_async16(a_hi + off, sp, nbytes);
-                        cp_async16(a_lo + off, sp + p.in_plane, nbytes);
-                    };
-                    if constexpr (CS == 64 || CS == 32) {          // one tap per thread: tl = 0 (64) or hf (32)
-                        const int tl = CS == 64 ? 0 : hf;
-                        const int src = row_of(g * tpg + tl);
+                const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) copy(hf * 4 + c, src, CS == 64 ? hf * 4 + c : c);
-                    } else if constexpr (CS == 16) {               // two taps per thread, two pieces each
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int src = row_of(g * 4 + hf * 2 + h);
-                            copy(hf * 4 + h * 2, src, 0);
-                            copy(hf * 4 + h * 2 + 1, src, 1);
-                        }
-                    } else if constexpr (CS == 8) {                // four taps per thread, one piece each
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) copy(hf * 4 + c, row_of(g * 8 + hf * 4 + c), 0);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int q = hf * 4 + c;
-                            const int tl = q / ppt, piece = q - tl * ppt;
-                            copy(q, tl < tpg ? row_of(g * tpg + tl) : -1, piece);
-                        }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t nbytes = srcs[j] >= 0 ? 16u : 0u;     // 0 -> hardware zero fill
+                    const uint32_t eo = (uint32_t)(srcs[j] < 0 ? 0 : srcs[j]) * (uint32_t)cin;
+                    cp_async16(a_hi + offs[j], in_hi + eo, nbytes);
+                    cp_async16(a_lo + offs[j], in_lo + eo, nbytes);
                 }
-                cp_async_arrive_noinc(full_a(stage));
+                cp_async_arrive_noinc(full_a(stage, pw));
                 if (trp) { tw += c1 - c0; ti += clock64() - c1; }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -306,7 +309,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             for (int tile = tile0; tile < ntiles; tile += tstep) {
                 if (nbr_tiles && tile + tstep < ntiles) load_nbr(tile + tstep);
                 const uint32_t cmask = chunks_of(tile);
-                for (int ch = 0; ch < nchunks; ++ch) {
+                const int rot = rot_of(tile);
+                for (int ci = 0; ci < nchunks; ++ci) {
+                    const int ch = ci + rot < nchunks ? ci + rot : ci + rot - nchunks;
                     if (!((cmask >> ch) & 1u)) continue;
                     mbar_wait(empty(stage), phase ^ 1u);
                     const uint32_t dst = base + stage * C::STAGE_BYTES + 2 * A_TILE_BYTES;
@@ -323,16 +328,22 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         // async proxy, so a fence.proxy.async has to sit between.  In the producers it lowers to MEMBAR.ALL.CTA and
         // stalls on their own in-flight copies; in the MMA lane it costs 130-650 clk per chunk that are serial with
         // MMA issue (round-1 timeline trace).  This lane has nothing else to do.
-        if (lane == 0) {
+        // Lanes 0..7 each wait for one producer warp's barrier (in parallel), lane 0 then fences and signals.
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < ntiles; tile += tstep) {
                 const uint32_t cmask = chunks_of(tile);
-                for (int ch = 0; ch < nchunks; ++ch) {
+                const int rot = rot_of(tile);
+                for (int ci = 0; ci < nchunks; ++ci) {
+                    const int ch = ci + rot < nchunks ? ci + rot : ci + rot - nchunks;
                     if (!((cmask >> ch) & 1u)) continue;
-                    mbar_wait(full_a(stage), phase);
-                    fence_proxy_async();
-                    mbar_arrive(ready_a(stage));
+                    if (lane < PROD_WARPS) mbar_wait(full_a(stage, lane), phase);
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_arrive(ready_a(stage));
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -350,7 +361,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         int acc = 0;
         uint32_t acc_phase = 0;
         int executed = 0, tiles_done = 0;
-        long long mw = 0, mi = 0, me = 0;
+        long long mw = 0, mi = 0, me = 0, mwb = 0;
         const bool trm = tr && leader;
         for (int tile = tile0; tile < ntiles; tile += tstep) {
             const uint32_t cmask = chunks_of(tile);
@@ -360,13 +371,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             if (trm) me += clock64() - c0;
             const uint32_t d_big = tmem_base + (uint32_t)(acc * C::ACC_COLS), d_small2 = d_big + (uint32_t)(2 * BN);
             uint32_t accum = 0u;
-            for (int ch = 0; ch < nchunks; ++ch) {
+            const int rot = rot_of(tile);
+            for (int ci = 0; ci < nchunks; ++ci) {
+                const int ch = ci + rot < nchunks ? ci + rot : ci + rot - nchunks;
                 if (!((cmask >> ch) & 1u)) continue;
                 c0 = trm ? clock64() : 0;
                 mbar_wait(ready_a(stage), phase);
+                const long long cb = trm ? clock64() : 0;
                 mbar_wait(full_b(stage), phase);
                 tc_fence_after();
                 const long long c1 = trm ? clock64() : 0;
+                if (trm) mwb += c1 - cb;
                 // channels beyond cin are zero in both operands: issue only the K=16 steps that carry data
                 const int ksteps = (p.dbg & 16) ? 0 : min(4, (min(tpg, p.taps - ch * tpg) * cin + 15) / 16);
                 const uint32_t ah = lo0 + (uint32_t)stage * kStageLo, al = ah + kTileLo, bh = al + kTileLo;
@@ -398,7 +413,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             ++tiles_done;
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
-        if (trm) { tr[6] = mw; tr[7] = mi; tr[8] = me; tr[9] = clock64(); tr[10] = executed; }
+        if (trm) { tr[6] = mw; tr[7] = mi; tr[8] = me; tr[9] = clock64(); tr[10] = executed; tr[12] = mwb; }
         if (p.counters && leader && executed) {
             atomicAdd(&p.counters[0], executed);
             atomicAdd(&p.counters[1], part == 0 ? tiles_done : 0);
@@ -418,8 +433,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                 tc_fence_after();
             }
             const int m = tile * BM + r;
+            // Tap split: the two CTAs hold partial sums of the SAME 128 rows.  Each finalises half of them - CTA 0
+            // rows 0..63 (its epilogue warps 0, 1), CTA 1 rows 64..127 (warps 2, 3) - and its other two warps
+            // ("givers") hand the partial sums of the rows it does not own to the peer: fp32 rows in an L2-resident
+            // scratch block, then a remote mbarrier arrive (release / acquire at cluster scope).  Half the bytes
+            // cross, in both directions at once, and the BN / split / store work is shared.
             float* prow = split ? p.scratch + ((size_t)tile * BM + r) * BN : nullptr;
-            if (split && part == 0) {           // leader: the peer's partial sums must be visible
+            const bool giver = split && ((warp >> 1) != part);
+            if (split && !giver) {              // keeper: the peer's partial sums of my rows must be visible
                 if (lane == 0) mbar_wait_cluster(peer_done, 0u);
                 __syncwarp();
             }
@@ -428,6 +449,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             for (int c0 = 0; c0 < BN; c0 += CW) {
                 uint32_t v[CW], u[CW], w[CW];
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + c0);
+                float4 q4[CW / 4];              // keeper: the peer's partial sums, requested before the TMEM loads
+                if (split && !giver) {
+#pragma unroll
+                    for (int j = 0; j < CW / 4; ++j) q4[j] = __ldcg((const float4*)(prow + c0 + 4 * j));   // L2
+                }
                 if (have_acc) {
                     tmem_ld<CW>(v, taddr);
                     tmem_ld<CW>(u, taddr + (uint32_t)BN);
@@ -448,7 +474,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                     const float small = __fadd_rn(__uint_as_float(u[j]), __uint_as_float(w[j]));
                     a[j] = __fadd_rn(__uint_as_float(v[j]), small * (1.f / kF16LoScale));
                 }
-                if (split && part != 0) {       // peer: hand the partial sums over, no epilogue
+                if (giver) {                    // hand the partial sums over, no epilogue for these rows here
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) *(float4*)(prow + c0 + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
                     continue;
@@ -456,7 +482,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                 if (split) {
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
-                        const float4 q = __ldcg((const float4*)(prow + c0 + j));     // L2 (the peer's SM wrote it)
+                        const float4 q = q4[j / 4];
                         a[j] = __fadd_rn(a[j], q.x); a[j + 1] = __fadd_rn(a[j + 1], q.y);
                         a[j + 2] = __fadd_rn(a[j + 2], q.z); a[j + 3] = __fadd_rn(a[j + 3], q.w);
                     }
@@ -520,7 +546,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                     }
                 }
             }
-            if (split && part != 0) mbar_arrive_remote(peer_done, 0u);     // every thread releases its own stores
+            if (giver) mbar_arrive_remote(peer_done, (uint32_t)(part ^ 1));    // every thread releases its own stores
             if (have_acc && ++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
         if (tr && threadIdx.x == 0) tr[11] = clock64();
@@ -536,10 +562,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
     cluster_sync_all();           // no CTA of the cluster exits while its peer may still arrive on its barriers
 }
 
-template <int TABLE, int BN, int CS>
+template <int TABLE, int BN>
 static int launch3(const Args& a, cudaStream_t stream) {
     using C = Cfg3<BN>;
-    auto kern = spconv_split_kernel<TABLE, BN, CS>;
+    auto kern = spconv_split_kernel<TABLE, BN>;
     // Persistent CTAs in clusters of two, one CTA per SM (225 KB of shared memory): the grid must not exceed what is
     // co-resident - GPCs with an odd number of free SMs cannot host a last cluster, and a cluster left over for a
     // second wave would double the kernel's time.
@@ -563,22 +589,12 @@ static int launch3(const Args& a, cudaStream_t stream) {
     return sassd_check_launch();
 }
 
-// the network's (stored cin, cout) shapes get compile-time producers; anything else the run-time ones
 template <int TABLE>
 static int dispatch3(const Args& a, cudaStream_t s) {
-    const int bn = a.cout <= 16 ? 16 : (a.cout <= 32 ? 32 : 64);
-    if (a.cout > 64) return SASSD_ERR_UNSUPPORTED;
-    if (a.cin == 64 && bn == 64) return launch3<TABLE, 64, 64>(a, s);
-    if (TABLE) {
-        if (a.cin == 32 && bn == 64) return launch3<TABLE, 64, 32>(a, s);
-        if (a.cin == 32 && bn == 32) return launch3<TABLE, 32, 32>(a, s);
-        if (a.cin == 16 && bn == 32) return launch3<TABLE, 32, 16>(a, s);
-        if (a.cin == 16 && bn == 16) return launch3<TABLE, 16, 16>(a, s);
-        if (a.cin == 8 && bn == 16) return launch3<TABLE, 16, 8>(a, s);
-    }
-    if (bn == 16) return launch3<TABLE, 16, 0>(a, s);
-    if (bn == 32) return launch3<TABLE, 32, 0>(a, s);
-    return launch3<TABLE, 64, 0>(a, s);
+    if (a.cout <= 16) return launch3<TABLE, 16>(a, s);
+    if (a.cout <= 32) return launch3<TABLE, 32>(a, s);
+    if (a.cout <= 64) return launch3<TABLE, 64>(a, s);
+    return SASSD_ERR_UNSUPPORTED;
 }
 
 }  // namespace sps
@@ -666,12 +682,12 @@ extern "C" int sassd_spconv_f16x3(const sassd_spconv_desc* d, const void* in_spl
             cudaStreamSynchronize((cudaStream_t)stream_);
             cudaMemcpy(h.data(), trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
             fprintf(stderr, "SPS_TRACE rows_cap %d cin %d cout %d: cta  prologue  kernel | prod: wait_empty issue wait_nbr end | "
-                            "mma: wait_data issue wait_acc end chunks | epi_end\n", d->rows_cap, d->cin, d->cout);
+                            "mma: wait_data(of which B) issue wait_acc end chunks | epi_end\n", d->rows_cap, d->cin, d->cout);
             for (int c = 0; c < 148; c += (c < 4 ? 1 : 37)) {
                 const long long* q = &h[(size_t)c * 16];
                 if (!q[0]) continue;
-                fprintf(stderr, "SPS_TRACE %3d %8lld %8lld | %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld %4lld | %8lld\n", c,
-                        q[1] - q[0], (q[11] ? q[11] : q[9]) - q[0], q[2], q[3], q[4], q[5] ? q[5] - q[0] : 0, q[6], q[7], q[8],
+                fprintf(stderr, "SPS_TRACE %3d %8lld %8lld | %8lld %8lld %8lld %8lld | %8lld (%lld) %8lld %8lld %8lld %4lld | %8lld\n", c,
+                        q[1] - q[0], (q[11] ? q[11] : q[9]) - q[0], q[2], q[3], q[4], q[5] ? q[5] - q[0] : 0, q[6], q[12], q[7], q[8],
                         q[9] ? q[9] - q[0] : 0, q[10], q[11] ? q[11] - q[0] : 0);
             }
             return rc;

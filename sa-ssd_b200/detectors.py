@@ -178,7 +178,7 @@ class SingleStageDetector(nn.Module):
         data-dependent size already lives on the device, so the ~65 launches of a step become one graph
         launch.  Steps whose shape does not fit fall back to the eager path."""
         self._graph_args = (int(batch), int(max_points_per_frame))
-        self._graph = _GraphedStep(self, batch, max_points_per_frame)
+        self._graph = _GraphedStep(self, batch, max_points_per_frame, latency=True)
         return self._graph
 
     def disable_cuda_graph(self):
@@ -222,7 +222,7 @@ class SingleStageDetector(nn.Module):
         dev = next(self.parameters()).device
         hp, ho, counts = self.stage_points(points_list)
         if self._graph is None and self._graph_args is not None:     # dropped by a weight / precision change
-            self._graph = _GraphedStep(self, *self._graph_args)
+            self._graph = _GraphedStep(self, *self._graph_args, latency=True)
         g = self._graph
         if g is not None and not return_aux and g.fits(len(points_list), counts):
             bbs, scs, lbs = g.run_host(hp, ho, sum(counts))
@@ -257,7 +257,10 @@ def _stage_into(hp, ho, points_list, counts):
 class _GraphedStep:
     """One captured step of SingleStageDetector.forward_device with static input/output buffers."""
 
-    def __init__(self, model, batch, max_points_per_frame):
+    def __init__(self, model, batch, max_points_per_frame, latency=False):
+        """latency=True: this step will run alone on the GPU (enable_cuda_graph / forward_points): the dense convs walk
+        the computed tiles first so that the constant-region tiles shorten every layer; False (detect_stream slots,
+        several steps in flight): round-robin tiles, the SMs a layer leaves idle serve the other steps."""
         dev = next(model.parameters()).device
         self.model, self.batch, self.maxpts = model, int(batch), int(max_points_per_frame)
         self.cap = self.batch * self.maxpts
@@ -268,6 +271,7 @@ class _GraphedStep:
         self.ws = ops.Workspace()
         self.stream = torch.cuda.Stream(device=dev)
         shared_ws, ops._WS = ops._WS, self.ws
+        order0, ops.CONV2D_TILE_ORDER = ops.CONV2D_TILE_ORDER, 1 if latency else 0
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -282,6 +286,7 @@ class _GraphedStep:
                                                                                     self.batch, self.maxpts)
         finally:
             ops._WS = shared_ws
+            ops.CONV2D_TILE_ORDER = order0
         self.h_det = torch.empty(self.det.shape, dtype=torch.float32, pin_memory=True)
         self.h_nd = torch.empty(self.d_ndet.shape, dtype=torch.int32, pin_memory=True)
         self.h_status = torch.empty((1,), dtype=torch.int32, pin_memory=True)

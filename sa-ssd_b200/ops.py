@@ -389,6 +389,7 @@ class SplitMap:
 
 
 TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # constant-region tile skipping in the BEV convs
+CONV2D_TILE_ORDER = 0       # 1 while a latency-oriented step is captured (computed tiles first, see sassd_b200.h)
 CONV2D_COUNTERS = None     # bench instrumentation: {label: int32[2] device tensor} += tiles computed, += tiles
 _TILE_FAR = 1 << 20
 
@@ -455,6 +456,7 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     d = Conv2dDesc()
     d.batch, d.H, d.W, d.cin, d.cin_stored = B, H, W, cin, x.planes.shape[-1]
     d.cout, d.taps, d.relu = cout, taps, 1 if relu else 0
+    d.tile_order = CONV2D_TILE_ORDER
     osp = of = None
     if out_split:
         cs = (cout + 63) // 64 * 64
@@ -476,7 +478,7 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     if dist is not None:
         cvec = conv_constant(x.const, cin, weight, scale, shift, relu, cout)
     _call("sassd_conv2d_f16x3_occ", label, ctypes.byref(d), _ptr(x.planes), _ptr(wp), _ptr(scale), _ptr(shift), _ptr(of),
-          _ptr(osp), _ptr(dist), reach, _ptr(cvec), _ptr(CONV2D_COUNTERS.get(label) if CONV2D_COUNTERS else None),
+          _ptr(osp), _ptr(dist), reach, _ptr(cvec), _ptr(CONV2D_COUNTERS.get(label) if CONV2D_COUNTERS is not None else None),
           _stream())
     return (SplitMap(osp, cout, dist, reach, cvec) if osp is not None else None), of
 

@@ -23,7 +23,7 @@ CFG = dict(voxel_size=[0.05, 0.05, 0.1], pc_range=[0, -40., -3., 70.4, 40., 1.],
 
 # Calibration clouds = every cloud the parity tests, smoke() and bench.py use (seed, fov, azimuth step), so that the
 # bound below holds on all of them: ~20 k-point frames, the 5 k / 120 k density end points and the small smoke frame.
-CALIB_CLOUDS = [(s, 28.0, 0.1728) for s in (0, 1, 2, 3, 6, 7, 9)] + [(11, 28.0, 0.6912), (12, 180.0, 0.1728),
+CALIB_CLOUDS = [(s, 28.0, 0.1728) for s in range(16)] + [(11, 28.0, 0.6912), (12, 180.0, 0.1728),
                                                                      (1, 20.0, 0.3456)]
 OUTLIER_SIGMAS = 6.0
 
