@@ -93,7 +93,7 @@ def make_synthetic_state_dict(seed=0, num_class=1, num_filters=256, bev_in=320, 
     # three classes triple the anchors and take the max over classes: lower the bias so that the guided-anchor and
     # detection counts stay in the range of a trained model (and below the fixed result capacity)
     sd[p + "conv_cls.bias"] = torch.randn(na * num_class, generator=g) * 0.05 + cls_bias - (0.9 if num_class > 1 else 0.0)
-    sd[p + "conv_box.weight"] = torch.randn(na * 7, num_filters, 1, 1, generator=g) * s * 1.5
+    sd[p + "conv_box.weight"] = torch.randn(na * 7, num_filters, 1, 1, generator=g) * s * 1.0
     sd[p + "conv_box.bias"] = torch.randn(na * 7, generator=g) * 0.02
     sd[p + "conv_dir_cls.weight"] = torch.randn(na * 2, num_filters, 1, 1, generator=g) * s
     sd[p + "conv_dir_cls.bias"] = torch.randn(na * 2, generator=g) * 0.05

@@ -41,6 +41,13 @@ struct Cfg2 {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
     static constexpr int ACC_BUFS = (4 * BN <= 512) ? 2 : 1;
+    // Epilogue warps.  BN = 256 has a single accumulator buffer (2 x 256 columns = all of TMEM), so the next tile's MMAs
+    // wait until the epilogue has READ the accumulators: eight warps (two per TMEM lane quarter, 128 columns each) pull
+    // everything into registers first - ~1.5k clk instead of ~10k (profiles/r2_dense_epilogue.md) - then do the math.
+    static constexpr int EW = (BN >= 256) ? 8 : 4;
+    static constexpr int CPW = BN * 4 / EW;                  // accumulator columns per epilogue warp
+    static constexpr int THREADS = (EW + 2) * 32;
+    static constexpr int W_LOAD = EW, W_ISSUE = EW + 1;
     static constexpr int TMEM_COLS = (ACC_BUFS * 2 * BN < 32) ? 32 : ACC_BUFS * 2 * BN;
     // epilogue staging for the TMA store of the split output: per warp 2 buffers x (hi 2 KB + lo 2 KB)
     static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 2 * 4096;
@@ -201,8 +208,122 @@ __device__ __forceinline__ void drain_tile(const Conv2dArgs& p, const CUtensorMa
     }
 }
 
+// Epilogue of the columns [col0, col0 + CPW) of one 8x16-pixel tile for the warp that owns TMEM lane quarter `quad`:
+// ALL of its accumulator columns are read into registers first (big + small/2048 combined, so CPW fp32 registers),
+// then the accumulator buffer is released to the MMA warp, and only then comes the BN / ReLU / split math and the TMA
+// stores (same arithmetic and store path as drain_tile).  double_buf: this warp owns two staging buffers.
+template <int BN, int CPW, class Release>
+__device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMap* omap, uint32_t tmem_acc, int quad,
+                                           int col0, int lane, int b, int ty, int tx, uint32_t my_stage, bool double_buf,
+                                           uint32_t& store_it, Release&& release, bool const_tile) {
+    const int r = quad * 32 + lane;
+    const int py = r / TILE_W, px = r % TILE_W;
+    const int y = ty * TILE_H + py, x = tx * TILE_W + px;
+    const bool valid = y < p.H && x < p.W;
+    const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+    const uint32_t row_off = (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+    const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
+    constexpr int CW = 32;
+    float acc[CPW];
+    if (!const_tile) {
+#pragma unroll
+        for (int s0 = 0; s0 < CPW; s0 += CW) {
+            uint32_t v[CW], u[CW];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(col0 + s0);
+            tmem_ld<CW>(v, taddr);
+            tmem_ld<CW>(u, taddr + (uint32_t)BN);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+                acc[s0 + j] = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]) * (1.f / kF16LoScale));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release();           // accumulators are in registers: the next tile's MMAs may start
+    }
+#pragma unroll
+    for (int s0 = 0; s0 < CPW; s0 += CW) {
+        const int c0 = col0 + s0;
+        float o[CW];
+        if (const_tile) {         // constant input region: the output is the layer's precomputed constant vector
+#pragma unroll
+            for (int j = 0; j < CW; ++j) o[j] = (c0 + j) < p.cout ? __ldg(&p.cvec[c0 + j]) : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+                const int n = c0 + j;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (vec_ss) {
+                    if (n < p.cout) {
+                        sc = __ldg((const float4*)(p.scale + n));
+                        sh = __ldg((const float4*)(p.shift + n));
+                    }
+                } else {
+                    if (p.scale) {
+                        if (n + 0 < p.cout) sc.x = __ldg(&p.scale[n + 0]);
+                        if (n + 1 < p.cout) sc.y = __ldg(&p.scale[n + 1]);
+                        if (n + 2 < p.cout) sc.z = __ldg(&p.scale[n + 2]);
+                        if (n + 3 < p.cout) sc.w = __ldg(&p.scale[n + 3]);
+                    }
+                    if (p.shift) {
+                        if (n + 0 < p.cout) sh.x = __ldg(&p.shift[n + 0]);
+                        if (n + 1 < p.cout) sh.y = __ldg(&p.shift[n + 1]);
+                        if (n + 2 < p.cout) sh.z = __ldg(&p.shift[n + 2]);
+                        if (n + 3 < p.cout) sh.w = __ldg(&p.shift[n + 3]);
+                    }
+                }
+                const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float val = fmaf(acc[s0 + j + e], scs[e], shs[e]);
+                    if (p.relu) val = fmaxf(val, 0.f);
+                    o[j + e] = (n + e) < p.cout ? val : 0.f;
+                }
+            }
+        }
+        if (p.out_f32 && valid) {
+            float* orow = p.out_f32 + pix * p.out_f32_stride;
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+                const int n = c0 + j;
+                if (n + 3 < p.out_f32_stride) *(float4*)(orow + n) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                else
+                    for (int e = 0; e < 4; ++e)
+                        if (n + e < p.out_f32_stride) orow[n + e] = o[j + e];
+            }
+        }
+        if (p.out_split && c0 < p.out_split_ch) {
+            const uint32_t buf = my_stage + (double_buf ? (store_it & 1u) * 4096u : 0u);
+            if (store_it >= (double_buf ? 2u : 1u)) {      // the store that last used this buffer has finished reading it
+                if (lane == 0) { if (double_buf) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_f16x2(o[8 * q + 0], o[8 * q + 1], h0, l0);
+                split_f16x2(o[8 * q + 2], o[8 * q + 3], h1, l1);
+                split_f16x2(o[8 * q + 4], o[8 * q + 5], h2, l2);
+                split_f16x2(o[8 * q + 6], o[8 * q + 7], h3, l3);
+                const uint32_t dst = buf + row_off + (((uint32_t)q ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2048u), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int oy = ty * TILE_H + 2 * quad, ox = tx * TILE_W;
+                tma_store_4d(omap, c0, ox, oy, b, buf);
+                tma_store_4d(omap, c0, ox, oy, p.batch + b, buf + 2048u);
+                bulk_commit_group();
+            }
+            ++store_it;
+        }
+    }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(THREADS2, 1)
+__global__ void __launch_bounds__(Cfg2<BN>::THREADS, 1)
 conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap omap, const Conv2dArgs p) {
     using C = Cfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -228,12 +349,12 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), EPI_WARPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), C::EW); }
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
         if (p.out_split) asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
     }
-    if (warp == WARP_ISSUE) {
+    if (warp == C::W_ISSUE) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                      "r"((uint32_t)C::TMEM_COLS)
                      : "memory");
@@ -269,7 +390,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     }
     auto tile_at = [&](int k) { return use_order ? (int)order[k] : k; };
 
-    if (warp == WARP_LOAD) {
+    if (warp == C::W_LOAD) {
         if (lane == 0) {
             int stage = 0, issued = 0;
             uint32_t phase = 0;
@@ -306,7 +427,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 }
             }
         }
-    } else if (warp == WARP_ISSUE) {
+    } else if (warp == C::W_ISSUE) {
         // Warp-convergent loop (uniform datapath), one elected lane issues.  Round 2: this loop, not the tensor pipe,
         // was the bound - rebuilding four 64-bit descriptors per K=16 step plus a run-time debug variant cost ~60 SASS
         // instructions per three MMAs (profiles/r2_mma_issue_probe.md) - so a descriptor is now a per-stage low word
@@ -380,11 +501,13 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             if (computed) atomicAdd(&p.counters[0], computed);
             if (blockIdx.x == 0) atomicAdd(&p.counters[1], ntiles);
         }
-    } else if (warp < EPI_WARPS) {
+    } else if (warp < C::EW) {
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t store_it = 0;
-        const uint32_t my_stage = ostage_base + (uint32_t)warp * 8192u;
+        const int quad = warp & 3, col0 = (warp >> 2) * C::CPW;          // TMEM lane quarter, first column of this warp
+        constexpr bool kDoubleBuf = C::EW == 4;                          // 32 KB of staging: 4 x 2 x 4 KB or 8 x 4 KB
+        const uint32_t my_stage = ostage_base + (uint32_t)warp * (uint32_t)(C::OUT_STAGE_BYTES / C::EW);
         long long* tr = (p.trace && threadIdx.x == 0) ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
         long long e_wait = 0, e_drain = 0;
         for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
@@ -392,7 +515,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             const int b = tile / (tiles_y * tiles_x);
             const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
             if (tile_is_constant(p, tile, ty, tx, tiles_y, tiles_x)) {      // no MMAs ran for this tile
-                drain_tile<BN>(p, &omap, 0u, warp, lane, b, ty, tx, true, my_stage, store_it, [] {}, true);
+                drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {}, true);
                 continue;
             }
             const long long c0 = tr ? clock64() : 0;
@@ -401,8 +524,8 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             tc_fence_after();
             const long long c1 = tr ? clock64() : 0;
             const uint32_t bar = tmem_empty(acc);
-            drain_tile<BN>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), warp, lane, b, ty, tx, true, my_stage, store_it,
-                           [bar] { mbar_arrive(bar); });
+            drain_cols<BN, C::CPW>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), quad, col0, lane, b, ty, tx, my_stage,
+                                   kDoubleBuf, store_it, [bar] { mbar_arrive(bar); }, false);
             if (tr) { e_wait += c1 - c0; e_drain += clock64() - c1; }
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
@@ -413,7 +536,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
-    if (warp == WARP_ISSUE) {
+    if (warp == C::W_ISSUE) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                      : "memory");
@@ -669,7 +792,7 @@ static int launch2(const CUtensorMap& map, const CUtensorMap& omap, const Conv2d
     }
     const int tiles = a.batch * sassd_div_up(a.H, TILE_H) * sassd_div_up(a.W, TILE_W);
     const int grid = tiles < 148 ? tiles : 148;
-    if (launch_pdl(kern, dim3(grid), dim3(THREADS2), C::SMEM_BYTES, stream, map, omap, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
+    if (launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, map, omap, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
 }
 

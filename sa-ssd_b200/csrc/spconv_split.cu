@@ -187,20 +187,33 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
     const int ntiles = (M + BM - 1) / BM;
     long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
     if (tr && threadIdx.x == 0) { tr[0] = t_start; tr[1] = clock64(); }
-    // Work decomposition, uniform over the grid.  Tap split: cluster q owns tile q, its two CTAs share the chunks.
+    // Work decomposition, uniform over the grid: R full rounds of one tile per CTA, then the remaining `rem` tiles.  A
+    // layer that has at most half as many tiles as there are CTAs (one frame at a time: 42-74 tiles) runs as a TAP
+    // SPLIT: cluster q owns tile q and its two CTAs share that tile's chunks, so a 45-tile layer occupies 90 SMs with
+    // half the chunk chain each.  (Splitting only the last partial round of a LARGE layer was measured too - 933
+    // tiles: 6.5 instead of 7 rounds - and lost what it gained to the hand-over at the very end of the kernel, where
+    // nothing overlaps it: B=16 sparse stage 1.178 -> 1.233 ms.  Hence R == 0.)
     const uint32_t crank = cluster_ctarank();
-    const bool split = TABLE && p.scratch && !(p.dbg & 2) && nchunks > 1 && 2 * ntiles <= (int)gridDim.x &&
-                       ntiles <= SPLIT_TILES_MAX;
-    const int tile0 = split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int tstep = split ? ntiles : (int)gridDim.x;        // split: at most one tile per cluster
-    const int part = split ? (int)crank : 0, nparts = split ? 2 : 1;
-    auto chunks_of = [&](int tile) {
+    const int G = (int)gridDim.x;
+    const int R = ntiles / G, rem = ntiles - R * G;
+    const bool tail_split = TABLE && p.scratch && !(p.dbg & 2) && nchunks > 1 && R == 0 && rem > 0 && 2 * rem <= G &&
+                            rem <= SPLIT_TILES_MAX;
+    const int n_items = R + ((tail_split ? (int)(blockIdx.x >> 1) < rem : (int)blockIdx.x < rem) ? 1 : 0);
+    struct Item { int tile, part, nparts; };
+    auto item_at = [&](int i) {
+        Item it;
+        if (i < R) { it.tile = (int)blockIdx.x + i * G; it.part = 0; it.nparts = 1; }
+        else if (tail_split) { it.tile = R * G + (int)(blockIdx.x >> 1); it.part = (int)crank; it.nparts = 2; }
+        else { it.tile = R * G + (int)blockIdx.x; it.part = 0; it.nparts = 1; }
+        return it;
+    };
+    auto chunks_of = [&](const Item& it) {
         uint32_t tm = all_taps;
         if (TABLE && p.tile_mask && !(p.dbg & 1)) {
-            tm = (uint32_t)__ldg(&p.tile_mask[tile]) & all_taps;
+            tm = (uint32_t)__ldg(&p.tile_mask[it.tile]) & all_taps;
             if (!tm) tm = 1u;       // a tile without any pair still has to produce act(shift): run one (all-zero) chunk
         }
-        return ChunkSet(tm, tpg, nchunks, part, nparts).mask;
+        return ChunkSet(tm, tpg, nchunks, it.part, it.nparts).mask;
     };
     // Every CTA streams the same weight chunks.  If they all walked the taps in the same order they would ask the
     // same few L2 lines for the same 16 KB at the same time; each tile therefore starts at a different tap
@@ -237,12 +250,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         uint32_t nb_phase = 0;
         long long tw = 0, ti = 0, tn = 0;
         const bool trp = tr && pw == 0 && lane == 0;
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
+        for (int ii = 0; ii < n_items; ++ii) {
+            const Item item = item_at(ii);
+            const int tile = item.tile;
             // rows of the table the loader thread copied for this tile (whole 16-byte units only)
             const int rows_here = min(BM, p.rows_cap - tile * BM);
             const int rows_copied = nbr_tiles ? ((rows_here * p.taps * 4) & ~15) / (p.taps * 4) : 0;
             const int* ntile = nbr_smem + nb * (C::NBR_TILE_BYTES / 4);
-            const uint32_t cmask = chunks_of(tile);
+            const uint32_t cmask = chunks_of(item);
             const int m0 = tile * BM + pw * 16 + oct;       // global row of j = 0
             long long c0 = trp ? clock64() : 0;
             if (nbr_tiles) {
@@ -251,26 +266,40 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             }
             if (trp) tn += clock64() - c0;
             const int rot = rot_of(tile);
-            for (int gi = 0; gi < nchunks; ++gi) {
-                const int g = gi + rot < nchunks ? gi + rot : gi + rot - nchunks;
-                if (!((cmask >> g) & 1u)) continue;
-                // the four neighbour indices of this chunk before the wait (they do not depend on the stage)
+            auto chunk_at = [&](int gi) { return gi + rot < nchunks ? gi + rot : gi + rot - nchunks; };
+            auto next_active = [&](int gi) {            // next position of the rotated walk whose chunk is executed
+                for (++gi; gi < nchunks; ++gi)
+                    if ((cmask >> chunk_at(gi)) & 1u) break;
+                return gi;
+            };
+            // The neighbour indices are shared-memory loads, i.e. they go through the same LSU queue as the cp.async
+            // copies: issued after a chunk's copies they return only when those have drained (~a chunk period - the
+            // trace showed ~850 clk per chunk of this thread waiting for four LDS).  So the indices of the NEXT chunk are
+            // requested BEFORE this chunk's copies are queued.
+            auto load_srcs = [&](int g, int (&dst)[4]) {
                 const int t = g * tpg + tl;
                 const bool tap_ok = tl < tpg && t < p.taps && !(p.dbg & 32);
-                int srcs[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int m = m0 + 4 * j;
-                    srcs[j] = -1;
+                    dst[j] = -1;
                     if (tap_ok && m < M)
-                        srcs[j] = TABLE ? ((nbr_tiles && pw * 16 + j * 4 + oct < rows_copied) ? ntile[rowt[j] + t]
-                                                                                           : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
+                        dst[j] = TABLE ? ((nbr_tiles && pw * 16 + j * 4 + oct < rows_copied) ? ntile[rowt[j] + t]
+                                                                                          : __ldg(&p.nbr[(size_t)m * p.taps + t])) : m;
                 }
+            };
+            int gi = next_active(-1);
+            int srcs[4] = {-1, -1, -1, -1};
+            if (gi < nchunks) load_srcs(chunk_at(gi), srcs);
+            while (gi < nchunks) {
+                const int gi_next = next_active(gi);
                 // one lane polls the mbarrier, the warp follows
                 c0 = trp ? clock64() : 0;
                 if (lane == 0) mbar_wait(empty(stage), phase ^ 1u);
                 __syncwarp();
                 const long long c1 = trp ? clock64() : 0;
+                int nxt[4] = {-1, -1, -1, -1};
+                if (gi_next < nchunks) load_srcs(chunk_at(gi_next), nxt);
                 const uint32_t a_hi = base + stage * C::STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -282,6 +311,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                 cp_async_arrive_noinc(full_a(stage, pw));
                 if (trp) { tw += c1 - c0; ti += clock64() - c1; }
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) srcs[j] = nxt[j];
+                gi = gi_next;
             }
             if (nbr_tiles) {
                 __syncwarp();
@@ -305,10 +337,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                 if (bytes) bulk_g2s(nbr_base + nb * C::NBR_TILE_BYTES, p.nbr + (size_t)tile * BM * p.taps, bytes, nbr_full(nb));
                 if (++nb == 2) { nb = 0; nb_phase ^= 1u; }
             };
-            if (nbr_tiles && tile0 < ntiles) load_nbr(tile0);
-            for (int tile = tile0; tile < ntiles; tile += tstep) {
-                if (nbr_tiles && tile + tstep < ntiles) load_nbr(tile + tstep);
-                const uint32_t cmask = chunks_of(tile);
+            if (nbr_tiles && n_items > 0) load_nbr(item_at(0).tile);
+            for (int ii = 0; ii < n_items; ++ii) {
+                const Item item = item_at(ii);
+                const int tile = item.tile;
+                if (nbr_tiles && ii + 1 < n_items) load_nbr(item_at(ii + 1).tile);
+                const uint32_t cmask = chunks_of(item);
                 const int rot = rot_of(tile);
                 for (int ci = 0; ci < nchunks; ++ci) {
                     const int ch = ci + rot < nchunks ? ci + rot : ci + rot - nchunks;
@@ -332,8 +366,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile0; tile < ntiles; tile += tstep) {
-                const uint32_t cmask = chunks_of(tile);
+            for (int ii = 0; ii < n_items; ++ii) {
+                const Item item = item_at(ii);
+                const int tile = item.tile;
+                const uint32_t cmask = chunks_of(item);
                 const int rot = rot_of(tile);
                 for (int ci = 0; ci < nchunks; ++ci) {
                     const int ch = ci + rot < nchunks ? ci + rot : ci + rot - nchunks;
@@ -363,8 +399,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         int executed = 0, tiles_done = 0;
         long long mw = 0, mi = 0, me = 0, mwb = 0;
         const bool trm = tr && leader;
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
-            const uint32_t cmask = chunks_of(tile);
+        for (int ii = 0; ii < n_items; ++ii) {
+            const Item item = item_at(ii);
+            const int tile = item.tile, part = item.part;
+            const uint32_t cmask = chunks_of(item);
             long long c0 = trm ? clock64() : 0;
             mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
             tc_fence_after();
@@ -410,13 +448,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             }
             if (leader) mma_commit(tmem_full(acc));
             __syncwarp();
-            ++tiles_done;
+            if (part == 0) ++tiles_done;
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
         if (trm) { tr[6] = mw; tr[7] = mi; tr[8] = me; tr[9] = clock64(); tr[10] = executed; tr[12] = mwb; }
         if (p.counters && leader && executed) {
             atomicAdd(&p.counters[0], executed);
-            atomicAdd(&p.counters[1], part == 0 ? tiles_done : 0);
+            atomicAdd(&p.counters[1], tiles_done);
         }
     } else {
         // ===================== epilogue =====================
@@ -424,8 +462,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
         const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
-        for (int tile = tile0; tile < ntiles; tile += tstep) {
-            const uint32_t cmask = chunks_of(tile);
+        for (int ii = 0; ii < n_items; ++ii) {
+            const Item item = item_at(ii);
+            const int tile = item.tile, part = item.part;
+            const bool split = item.nparts == 2;
+            const uint32_t cmask = chunks_of(item);
             const bool have_acc = cmask != 0;       // a split peer may have been dealt no chunk at all
             if (have_acc) {
                 if (lane == 0) mbar_wait(tmem_full(acc), acc_phase);
@@ -438,7 +479,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             // ("givers") hand the partial sums of the rows it does not own to the peer: fp32 rows in an L2-resident
             // scratch block, then a remote mbarrier arrive (release / acquire at cluster scope).  Half the bytes
             // cross, in both directions at once, and the BN / split / store work is shared.
-            float* prow = split ? p.scratch + ((size_t)tile * BM + r) * BN : nullptr;
+            float* prow = split ? p.scratch + ((size_t)(tile - R * G) * BM + r) * BN : nullptr;
             const bool giver = split && ((warp >> 1) != part);
             if (split && !giver) {              // keeper: the peer's partial sums of my rows must be visible
                 if (lane == 0) mbar_wait_cluster(peer_done, 0u);
