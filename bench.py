@@ -389,6 +389,10 @@ def run_ours(args, rank, world, local):
         evs[i][0].record()
         det, nd, status, aux = step(i)
         evs[i][1].record()
+    # Ranks drift apart over the untimed L2 flushes between steps; line them up (untimed, on the device) so that the
+    # gather's events time the exchange itself and not the wait for a rank whose flushes ran late.  The step times
+    # themselves are already max-over-ranks below.
+    D.barrier()
     g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
     g0.record()
     det_all, nd_all = gather(det, nd)
@@ -453,8 +457,17 @@ def run_ours(args, rank, world, local):
         return
     # ---- per-kernel profile (rank 0): dominant kernel + sparse-conv roofline
     model.disable_cuda_graph()
-    prof, aux = profile_step(model, *staged[0][:2], B, staged[0][2])
-    tile_counts, sp_counts = count_step(model, *staged[0][:2], B, staged[0][2])
+    # the per-stage pass runs the kernels in the configuration of the graph `value` was measured on (one step at a
+    # time: computed tiles first, half-width dense units on small maps)
+    from sassd_b200 import ops as _ops
+    order0, _ops.CONV2D_TILE_ORDER = _ops.CONV2D_TILE_ORDER, (1 if graph is not None else _ops.CONV2D_TILE_ORDER)
+    try:
+        prof, aux = profile_step(model, *staged[0][:2], B, staged[0][2])
+        tile_counts, sp_counts = count_step(model, *staged[0][:2], B, staged[0][2])
+    finally:
+        _ops.CONV2D_TILE_ORDER = order0
+    tiles_map = B * 25 * 11
+    nsplit_on = graph is not None and tiles_map <= _ops.CONV2D_NSPLIT_MAX_TILES and args.precision == "f16x3"
     peaks = load_peaks()
     H, W = 200, 176
     dom = max(prof.items(), key=lambda kv: kv[1]["ms_total_per_step"])
@@ -472,7 +485,8 @@ def run_ours(args, rank, world, local):
         peak = peaks["bf16_tflops_sustained"]
         kname = {"fp32": "gconv_ffma_kernel<CONV2D,128,16>", "tf32x3": "tc::gconv_tc_kernel<CONV2D,256,1,TF32X3>",
                  "mixed": "tc::gconv_tc_kernel<CONV2D,256,1,TF32X3>",
-                 "f16x3": "tma::conv2d_tma_kernel<256>" if bev_key.startswith("conv2d_tma") else
+                 "f16x3": ("tma::conv2d_tma_kernel<128> (half-width units)" if nsplit_on else "tma::conv2d_tma_kernel<256>")
+                          if bev_key.startswith("conv2d_tma") else
                           "tc::gconv_tc_kernel<CONV2D,256,1,F16X3>"}[args.precision]
         passes = {"fp32": "fp32 FFMA (no tensor cores)", "tf32x3": "3 TF32 MMA passes per algorithmic flop",
                   "mixed": "3 TF32 MMA passes per algorithmic flop",

@@ -176,6 +176,10 @@ typedef struct {
     int32_t tile_order;            /* sassd_conv2d_f16x3_occ: 0 = tiles round-robin over the CTAs (best with several steps
                                       in flight), 1 = computed tiles first, constant tiles after (best for one step at a
                                       time: no CTA gets two computed tiles while others only store constants) */
+    int32_t n_split;               /* 0 / 1 = a work unit is a whole tile (all cout channels); 2 (cout > 128 only) = a unit
+                                      is one half of a tile's output channels, N = 128 instructions: finer units for one
+                                      step at a time on maps of a few hundred tiles (B <= 4), where whole tiles quantise
+                                      badly over 148 SMs; costs a second read of the activation tile from L2 */
 } sassd_conv2d_desc;
 int sassd_conv2d_f16x3(const sassd_conv2d_desc* host_desc, const void* in_split, const void* wpack, const float* scale,
                        const float* shift, float* out_f32, void* out_split, sassd_stream_t stream);

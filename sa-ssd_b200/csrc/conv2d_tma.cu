@@ -31,13 +31,14 @@ using namespace tc;
 
 constexpr int TILE_H = SASSD_CONV2D_TILE_H, TILE_W = SASSD_CONV2D_TILE_W;   // 8 x 16 = 128 output pixels per tile
 constexpr int BKC = 64;                         // channels per chunk (one 128-byte fp16 row)
+constexpr int kConstTile = 1 << 30;             // tile reference flag: the tile only stores the layer's constant vector
 constexpr int EPI_WARPS = 4;
 constexpr int THREADS2 = (EPI_WARPS + 2) * 32;  // 192
 constexpr int WARP_LOAD = EPI_WARPS, WARP_ISSUE = EPI_WARPS + 1;
 
 template <int BN>
 struct Cfg2 {
-    static constexpr int B_TILE_BYTES = BN * 128;
+    static constexpr int B_TILE_BYTES = BN * 168;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
     static constexpr int ACC_BUFS = (4 * BN <= 512) ? 2 : 1;
@@ -87,10 +88,12 @@ struct Conv2dArgs {
     const float* cvec;    // output constant of the tiles that see a constant input (tile_dist > reach, not on the border)
     int reach;
     int* counters;        // optional [2]: += tiles computed (not stored as a constant), += tiles (bench instrumentation)
-    long long* trace;     // optional [grid][8] clock64 sums per CTA (SASSD_TMA_TRACE=n: n-th launch, timing experiments)
+    long long* trace;     // optional [grid][16] clock64 sums / globaltimer stamps per CTA (SASSD_TMA_TRACE=n: n-th launch, timing experiments)
     int tile_order;       // 1: computed tiles first (SASSD_TMA_ORDER=1), 0: round-robin
+    int nsplit;           // work units per tile: 1, or 2 = each unit computes BN of the 2*BN output channels (the weight
+                          // pack is the 2*BN-wide one; small maps, where whole tiles are too coarse to balance 148 SMs)
     int dbg;              // SASSD_TMA_DBG (timing experiments only): 1 = reuse stale B stages, 2 = reuse stale A stages,
-                          // 4 = plain MMAs (no operand collector)
+                          // 4 = plain MMAs (no operand collector), 8 = no TMA stores, 16 = no wait for the staging buffer
 };
 
 // True when tile (ty, tx) sees a constant input and its output is p.cvec (see sassd_conv2d_f16x3_occ in the header).
@@ -215,7 +218,8 @@ __device__ __forceinline__ void drain_tile(const Conv2dArgs& p, const CUtensorMa
 template <int BN, int CPW, class Release>
 __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMap* omap, uint32_t tmem_acc, int quad,
                                            int col0, int lane, int b, int ty, int tx, uint32_t my_stage, bool double_buf,
-                                           uint32_t& store_it, Release&& release, bool const_tile) {
+                                           uint32_t& store_it, Release&& release, bool const_tile, int n_off = 0,
+                                           long long* ph = nullptr) {
     const int r = quad * 32 + lane;
     const int py = r / TILE_W, px = r % TILE_W;
     const int y = ty * TILE_H + py, x = tx * TILE_W + px;
@@ -225,6 +229,8 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
     const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
     constexpr int CW = 32;
     float acc[CPW];
+    long long tq = ph ? clock64() : 0;
+    auto stamp = [&](int i) { if (ph) { const long long t = clock64(); ph[i] += t - tq; tq = t; } };
     if (!const_tile) {
 #pragma unroll
         for (int s0 = 0; s0 < CPW; s0 += CW) {
@@ -241,9 +247,10 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
         __syncwarp();
         if (lane == 0) release();           // accumulators are in registers: the next tile's MMAs may start
     }
+    stamp(0);
 #pragma unroll
     for (int s0 = 0; s0 < CPW; s0 += CW) {
-        const int c0 = col0 + s0;
+        const int c0 = n_off + col0 + s0;       // output channel of this slice's first column
         float o[CW];
         if (const_tile) {         // constant input region: the output is the layer's precomputed constant vector
 #pragma unroll
@@ -292,12 +299,14 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
                         if (n + e < p.out_f32_stride) orow[n + e] = o[j + e];
             }
         }
+        stamp(1);
         if (p.out_split && c0 < p.out_split_ch) {
             const uint32_t buf = my_stage + (double_buf ? (store_it & 1u) * 4096u : 0u);
-            if (store_it >= (double_buf ? 2u : 1u)) {      // the store that last used this buffer has finished reading it
+            if (store_it >= (double_buf ? 2u : 1u) && !(p.dbg & 16)) {   // the store that last used this buffer has read it
                 if (lane == 0) { if (double_buf) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>(); }
                 __syncwarp();
             }
+            stamp(2);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -309,14 +318,17 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2048u), "r"(l0), "r"(l1), "r"(l2), "r"(l3) : "memory");
             }
+            stamp(3);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            stamp(4);
+            if (lane == 0 && !(p.dbg & 8)) {
                 const int oy = ty * TILE_H + 2 * quad, ox = tx * TILE_W;
                 tma_store_4d(omap, c0, ox, oy, b, buf);
                 tma_store_4d(omap, c0, ox, oy, p.batch + b, buf + 2048u);
                 bulk_commit_group();
             }
+            stamp(5);
             ++store_it;
         }
     }
@@ -340,10 +352,12 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         (volatile uint32_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + C::OUT_STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
     pdl_launch_dependents();      // the next layer may be scheduled as this grid's CTAs retire
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + 7] = (long long)globaltimer_ns();
     // warp index through a shuffle so that the compiler knows it is warp-uniform (role loops on the uniform datapath)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int tiles_x = (p.W + TILE_W - 1) / TILE_W, tiles_y = (p.H + TILE_H - 1) / TILE_H;
     const int ntiles = p.batch * tiles_y * tiles_x;
+    const int nsplit = p.nsplit, nunits = ntiles * nsplit;      // work unit k: tile k / nsplit, output channels (k % nsplit) * BN ...
     const int kchunks = (p.cin + BKC - 1) / BKC;
     const int nchunks = p.taps * kchunks;
 
@@ -372,33 +386,72 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     // order[blockIdx.x + i * gridDim.x].  Measured: one step at a time 705 -> 776 frames/s, but four steps in flight
     // 1470 -> 1290 (the freed SMs are what the other frames' kernels run on), so round-robin is the default.
     uint16_t* order = (uint16_t*)(base_ptr + C::STAGES * C::STAGE_BYTES + C::OUT_STAGE_BYTES + 256);
-    const bool use_order = p.tile_order && p.tile_dist != nullptr && ntiles <= C::ORDER_CAP;
-    if (use_order) {
+    const bool small_map = p.tile_dist != nullptr && ntiles <= C::ORDER_CAP;
+    const bool use_order = p.tile_order && small_map;
+    // For maps of up to ORDER_CAP tiles warp 0 fetches every tile's distance in one batch of loads (one memory latency
+    // instead of one per tile and role) and keeps the verdicts as order[k] bit 15.
+    if (small_map) {
         if (warp == 0) {
-            int n = 0;
-            for (int pass = 0; pass < 2; ++pass)
-                for (int t0 = 0; t0 < ntiles; t0 += 32) {
-                    const int t = t0 + lane;
-                    const bool cst = t < ntiles && tile_is_constant(p, t, (t / tiles_x) % tiles_y, t % tiles_x, tiles_y, tiles_x);
-                    const bool take = t < ntiles && (cst == (pass == 1));
-                    const uint32_t m = __ballot_sync(0xffffffffu, take);
-                    if (take) order[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
-                    n += __popc(m);
+            constexpr int PER = (C::ORDER_CAP + 31) / 32;
+            int dist[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int t = i * 32 + lane;
+                dist[i] = t < ntiles ? __ldg(&p.tile_dist[t]) : 0;
+            }
+            uint32_t cst_bits = 0u;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                if (i * 32 < ntiles) {                                   // warp-uniform
+                    const int t = i * 32 + lane;
+                    bool cst = t < ntiles && dist[i] > p.reach;
+                    if (cst && p.reach >= 2) {                           // border tiles see the zero padding
+                        const int ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+                        cst = !(ty == 0 || ty == tiles_y - 1 || tx == 0 || tx == tiles_x - 1);
+                    }
+                    if (cst) cst_bits |= 1u << i;
                 }
+            }
+            if (use_order) {
+                int n = 0;
+                for (int pass = 0; pass < 2; ++pass)
+#pragma unroll 1
+                    for (int i = 0; i * 32 < ntiles; ++i) {
+                        const int t = i * 32 + lane;
+                        const bool cst = (cst_bits >> i) & 1u;
+                        const bool take = t < ntiles && (cst == (pass == 1));
+                        const uint32_t m = __ballot_sync(0xffffffffu, take);
+                        if (take) order[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(t | (cst ? 0x8000 : 0));
+                        n += __popc(m);
+                    }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i * 32 < ntiles; ++i) {
+                    const int t = i * 32 + lane;
+                    if (t < ntiles) order[t] = (uint16_t)(t | (((cst_bits >> i) & 1u) ? 0x8000 : 0));
+                }
+            }
         }
         __syncthreads();
     }
-    auto tile_at = [&](int k) { return use_order ? (int)order[k] : k; };
+    // tile_ref(k): the k-th tile in walking order, bit 15 set when it only stores the layer's constant
+    auto tile_ref = [&](int k) -> int {
+        if (small_map) { const int v = order[k]; return (v & 0x7fff) | ((v & 0x8000) << 15); }
+        if (!p.tile_dist) return k;
+        return tile_is_constant(p, k, (k / tiles_x) % tiles_y, k % tiles_x, tiles_y, tiles_x) ? (k | kConstTile) : k;
+    };
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + 8] = (long long)globaltimer_ns();
 
     if (warp == C::W_LOAD) {
         if (lane == 0) {
             int stage = 0, issued = 0;
             uint32_t phase = 0;
-            for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
-                const int tile = tile_at(k);
+            for (int k = blockIdx.x; k < nunits; k += gridDim.x) {
+                const int ref = tile_ref(k / nsplit), half = k % nsplit;
+                if (ref & kConstTile) continue;                                         // nothing to load
+                const int tile = ref;
                 const int b = tile / (tiles_y * tiles_x);
                 const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
-                if (tile_is_constant(p, tile, ty, tx, tiles_y, tiles_x)) continue;      // nothing to load
                 const int y0 = ty * TILE_H, x0 = tx * TILE_W;
                 for (int t = 0; t < p.taps; ++t) {
                     const int dy = p.taps == 9 ? t / 3 - 1 : 0, dx = p.taps == 9 ? t % 3 - 1 : 0;
@@ -415,12 +468,18 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                             tma_load_4d(a_hi, &amap, kc * BKC, x0 + dx, y0 + dy, b, full(stage));
                             tma_load_4d(a_lo, &amap, kc * BKC, x0 + dx, y0 + dy, p.batch + b, full(stage));
                         }
-                        const uint8_t* src = (const uint8_t*)p.wpack + (size_t)(t * kchunks + kc) * (2 * C::B_TILE_BYTES);
-                        constexpr uint32_t kPiece = (2 * C::B_TILE_BYTES >= 16384) ? 16384u : (uint32_t)(2 * C::B_TILE_BYTES);
+                        // pack: per (tap, chunk) [hi | lo], each nsplit * BN rows of 128 bytes; this unit's BN rows of each
+                        const uint8_t* src = (const uint8_t*)p.wpack +
+                                             (size_t)(t * kchunks + kc) * (size_t)(2 * nsplit) * C::B_TILE_BYTES +
+                                             (size_t)half * C::B_TILE_BYTES;
+                        constexpr uint32_t kPiece = (C::B_TILE_BYTES >= 16384) ? 16384u : (uint32_t)C::B_TILE_BYTES;
                         if (load_b) {
 #pragma unroll 1
-                            for (uint32_t o = 0; o < 2u * C::B_TILE_BYTES; o += kPiece)
-                                bulk_g2s(b_dst + o, src + o, kPiece, full(stage));
+                            for (int part = 0; part < 2; ++part)
+#pragma unroll 1
+                                for (uint32_t o = 0; o < (uint32_t)C::B_TILE_BYTES; o += kPiece)
+                                    bulk_g2s(b_dst + part * C::B_TILE_BYTES + o,
+                                             src + (size_t)part * nsplit * C::B_TILE_BYTES + o, kPiece, full(stage));
                         }
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -442,13 +501,12 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         int computed = 0;
-        long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+        long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
         long long t_acc = 0, t_full = 0, t_iss = 0;
         const long long t_begin = tr ? clock64() : 0;
-        for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
-            const int tile = tile_at(k);
-            if (tile_is_constant(p, tile, (tile / tiles_x) % tiles_y, tile % tiles_x, tiles_y, tiles_x)) continue;
-            ++computed;
+        for (int k = blockIdx.x; k < nunits; k += gridDim.x) {
+            if (tile_ref(k / nsplit) & kConstTile) continue;
+            if (k % nsplit == 0) ++computed;
             long long c0 = tr ? clock64() : 0;
             mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
             tc_fence_after();
@@ -508,14 +566,17 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         const int quad = warp & 3, col0 = (warp >> 2) * C::CPW;          // TMEM lane quarter, first column of this warp
         constexpr bool kDoubleBuf = C::EW == 4;                          // 32 KB of staging: 4 x 2 x 4 KB or 8 x 4 KB
         const uint32_t my_stage = ostage_base + (uint32_t)warp * (uint32_t)(C::OUT_STAGE_BYTES / C::EW);
-        long long* tr = (p.trace && threadIdx.x == 0) ? p.trace + (size_t)blockIdx.x * 8 : nullptr;
+        long long* tr = (p.trace && threadIdx.x == 0) ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
         long long e_wait = 0, e_drain = 0;
-        for (int k = blockIdx.x; k < ntiles; k += gridDim.x) {
-            const int tile = tile_at(k);
+        long long phase_clk[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = blockIdx.x; k < nunits; k += gridDim.x) {
+            const int ref = tile_ref(k / nsplit), n_off = (k % nsplit) * BN;
+            const int tile = ref & ~kConstTile;
             const int b = tile / (tiles_y * tiles_x);
             const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
-            if (tile_is_constant(p, tile, ty, tx, tiles_y, tiles_x)) {      // no MMAs ran for this tile
-                drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {}, true);
+            if (ref & kConstTile) {                                         // no MMAs ran for this tile
+                drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {}, true,
+                                       n_off);
                 continue;
             }
             const long long c0 = tr ? clock64() : 0;
@@ -525,17 +586,21 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             const long long c1 = tr ? clock64() : 0;
             const uint32_t bar = tmem_empty(acc);
             drain_cols<BN, C::CPW>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), quad, col0, lane, b, ty, tx, my_stage,
-                                   kDoubleBuf, store_it, [bar] { mbar_arrive(bar); }, false);
+                                   kDoubleBuf, store_it, [bar] { mbar_arrive(bar); }, false, n_off, tr ? phase_clk : nullptr);
             if (tr) { e_wait += c1 - c0; e_drain += clock64() - c1; }
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }
         }
-        if (tr) { tr[5] = e_wait; tr[6] = e_drain; }
+        if (tr) {
+            tr[5] = e_wait; tr[6] = e_drain;
+            for (int i = 0; i < 6; ++i) tr[10 + i] = phase_clk[i];
+        }
         if (lane == 0) bulk_wait_group_all();
         __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
+    if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + 9] = (long long)globaltimer_ns();
     if (warp == C::W_ISSUE) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
@@ -554,7 +619,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 // the pair); tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs; the peer's epilogue
 // warps release the accumulator with a remote arrive on the leader's tmem_empty barrier.
 constexpr int STAGES_2CTA = 3;
-constexpr int B_HALF_BYTES = 128 * 128;                                   // 128 of the 256 weight rows, one plane
+constexpr int B_HALF_BYTES = 128 * 168;                                   // 128 of the 256 weight rows, one plane
 constexpr int STAGE_2CTA_BYTES = 2 * A_TILE_BYTES + 2 * B_HALF_BYTES;     // 64 KB
 constexpr int OUT_STAGE_2CTA_BYTES = EPI_WARPS * 2 * 4096;
 constexpr int SMEM_2CTA_BYTES = STAGES_2CTA * STAGE_2CTA_BYTES + OUT_STAGE_2CTA_BYTES + 1024 + 256;
@@ -685,7 +750,7 @@ conv2d_tma_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_co
                         tma_load_4d_pair(a_hi, &amap, kc * BKC, x0 + dx, y0 + dy, b, bar);
                         tma_load_4d_pair(a_lo, &amap, kc * BKC, x0 + dx, y0 + dy, p.batch + b, bar);
                         // weight rows of this CTA's half: block (t, kc) = [hi 256 rows][lo 256 rows]
-                        const int row = (t * kchunks + kc) * 2 * BN + (int)rank * 128;
+                        const int row = (t * kchunks + kc) * 2 * BN + (int)rank * 168;
                         tma_load_2d_pair(b_hi, &bmap, 0, row, bar);
                         tma_load_2d_pair(b_lo, &bmap, 0, row + BN, bar);
                         if (++stage == STAGES_2CTA) { stage = 0; phase ^= 1u; }
@@ -790,8 +855,8 @@ static int launch2(const CUtensorMap& map, const CUtensorMap& omap, const Conv2d
             return SASSD_ERR_LAUNCH;
         configured = true;
     }
-    const int tiles = a.batch * sassd_div_up(a.H, TILE_H) * sassd_div_up(a.W, TILE_W);
-    const int grid = tiles < 148 ? tiles : 148;
+    const int units = a.batch * sassd_div_up(a.H, TILE_H) * sassd_div_up(a.W, TILE_W) * a.nsplit;
+    const int grid = units < 148 ? units : 148;
     if (launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, map, omap, a) != cudaSuccess) return SASSD_ERR_LAUNCH;
     return sassd_check_launch();
 }
@@ -844,13 +909,14 @@ extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in
     a.out_f32_stride = d->out_f32_stride; a.out_split_ch = d->out_split_ch;
     a.tile_dist = tile_dist; a.reach = reach; a.cvec = const_out; a.counters = counters;
     a.trace = nullptr;
+    a.nsplit = 1;
     static const int trace_call = [] { const char* e = getenv("SASSD_TMA_TRACE"); return e ? atoi(e) : 0; }();
     static long long* trace_buf = nullptr;
     static int trace_calls = 0;
     bool tracing = false;
-    if (trace_call && d->cout == 256 && d->taps == 9 && ++trace_calls == trace_call) {
-        if (!trace_buf) cudaMalloc(&trace_buf, 148 * 8 * sizeof(long long));
-        cudaMemsetAsync(trace_buf, 0, 148 * 8 * sizeof(long long), (cudaStream_t)stream_);
+    if (trace_call && d->cout == 256 && ++trace_calls == trace_call) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 148 * 16 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 148 * 16 * sizeof(long long), (cudaStream_t)stream_);
         a.trace = trace_buf;
         tracing = true;
     }
@@ -876,18 +942,43 @@ extern "C" int sassd_conv2d_f16x3_occ(const sassd_conv2d_desc* d, const void* in
     if (d->cout <= 128) return launch2<128>(map, omap, a, stream);
     // opt-in: measured equal to the single-CTA kernel (both sit at the chip's sustained tensor rate)
     static const bool use_pair = [] { const char* e = getenv("SASSD_TMA_PAIR"); return e && atoi(e) != 0; }();
+    // Small maps (B = 1: 275 tiles of which about half are computed) leave 148 SMs with one or two whole tiles each;
+    // in halves of 128 output channels (same weight pack, N = 128 instructions at their 64-clk floor, double-buffered
+    // accumulators, three operand stages) the computed work spreads evenly and the last epilogue is half as long:
+    // one step at a time +5 % (B=1), +15 % (B=4, 7.4 -> 7.5 waves instead of 8).  Nothing at B >= 8, and with several
+    // steps in flight it costs 2-4 % (a half-width unit re-reads the activation tile: 85 B/clk/SM from L2), so
+    // the throughput slots and the 1x1 layer (load/store bound: 0.036 -> 0.044 ms) keep whole tiles.
+    // Selected per launch by the caller (desc.n_split = 2); SASSD_TMA_NSPLIT_TILES=n forces it for maps of <= n tiles.
+    static const int nsplit_tiles = [] { const char* e = getenv("SASSD_TMA_NSPLIT_TILES"); return e ? atoi(e) : -1; }();
+    const int map_tiles = a.batch * sassd_div_up(a.H, TILE_H) * sassd_div_up(a.W, TILE_W);
+    auto dump_trace = [&] {      // timing experiment: per-CTA clock sums / time stamps of this launch -> stderr
+        std::vector<long long> h(148 * 16);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t0 = 0, t1 = 0;
+        for (int c = 0; c < 148; ++c) {
+            const long long* q = &h[(size_t)c * 16];
+            if (!q[7]) continue;
+            if (!t0 || q[7] < t0) t0 = q[7];
+            if (q[9] > t1) t1 = q[9];
+        }
+        fprintf(stderr, "TMA_TRACE B=%d nsplit=%d: first CTA start -> last CTA end %.2f us\n", d->batch, a.nsplit, (t1 - t0) * 1e-3);
+        fprintf(stderr, "TMA_TRACE cta | mma: wait_acc wait_full issue total units | epi(warp0): wait_full drain | ns: start prologue end\n");
+        for (int c = 0; c < 148; c += (c < 3 ? 1 : 48)) {
+            const long long* q = &h[(size_t)c * 16];
+            fprintf(stderr, "TMA_TRACE %3d | %8lld %8lld %8lld %8lld %3lld | %8lld %8lld | %6lld %6lld %6lld | epi phases: tmem %lld math %lld bufwait %lld split+sts %lld fence %lld tma %lld\n", c, q[0], q[1], q[2],
+                    q[3], q[4], q[5], q[6], q[7] - t0, q[8] - t0, q[9] - t0, q[10], q[11], q[12], q[13], q[14], q[15]);
+        }
+    };
+    if (!use_pair && (nsplit_tiles >= 0 ? map_tiles <= nsplit_tiles : d->n_split == 2)) {
+        a.nsplit = 2;
+        const int rc = launch2<128>(map, omap, a, stream);
+        if (tracing) dump_trace();
+        return rc;
+    }
     if (!use_pair) {
         const int rc = launch2<256>(map, omap, a, stream);
-        if (tracing) {       // timing experiment: per-CTA clock sums of this launch -> stderr
-            std::vector<long long> h(148 * 8);
-            cudaStreamSynchronize(stream);
-            cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "TMA_TRACE B=%d: cta | mma: wait_acc wait_full issue total tiles | epi(warp0): wait_full drain\n", d->batch);
-            for (int c = 0; c < 148; c += (c < 3 ? 1 : 48)) {
-                const long long* q = &h[(size_t)c * 8];
-                fprintf(stderr, "TMA_TRACE %3d | %8lld %8lld %8lld %8lld %3lld | %8lld %8lld\n", c, q[0], q[1], q[2], q[3], q[4], q[5], q[6]);
-            }
-        }
+        if (tracing) dump_trace();
         return rc;
     }
     // weight pack as a 2-D tensor of 128-byte rows (already in UMMA swizzled order: no TMA swizzle)

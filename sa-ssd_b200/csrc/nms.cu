@@ -141,59 +141,59 @@ __device__ __forceinline__ float rotated_iou(const float* box_a, const float* bo
 }
 
 // mask[(frame*n_cap + i) * colb_cap + cb] bit j <=> iou(i, cb*64+j) > thr ; tiles with cb >= rb only.
-// The grid is fixed (CUDA-graph friendly); each CTA walks the frame's live upper-triangle tiles,
-// whose number depends on the device-side candidate count.
-#define NMS_MASK_THREADS 1024   // 64 rows x 16 column groups of 4
+// The grid is fixed (CUDA-graph friendly); each CTA walks the frame's live upper-triangle work items, whose number
+// depends on the device-side candidate count.  A work item is a QUARTER of a 64x64 tile - 64 rows x 16 columns, one
+// pair per thread: the guided anchors of an object overlap each other heavily, so many pairs take the slow rotated
+// polygon-clipping path, and with four pairs per thread (round 1) a frame's handful of tiles kept six SMs busy for
+// ~40 us (profiles/r2_ncu_small_kernels.md).  Each item writes its own 16-bit quarter of the 64-bit mask words.
+#define NMS_MASK_THREADS 1024   // 64 rows x 16 columns
 __global__ void __launch_bounds__(NMS_MASK_THREADS)
 nms_mask_kernel(const float* __restrict__ boxes5, const int* __restrict__ d_n, int n_fixed, int n_cap, int colb_cap,
                 float thr, unsigned long long* __restrict__ mask) {
     const int f = blockIdx.y;
     const int n = d_n ? min(d_n[f], n_cap) : n_fixed;
     const int colb = (n + 63) / 64;
-    const int ntiles = colb * (colb + 1) / 2;
+    const int nitems = 4 * (colb * (colb + 1) / 2);
     const float* bx = boxes5 + (size_t)f * n_cap * 5;
-    __shared__ float s_col[64 * 5];
-    __shared__ unsigned long long s_bits[64];
-    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;   // row in tile, column group
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __shared__ float s_col[16 * 5];
+    __shared__ unsigned int s_bits[64];
+    const int r = threadIdx.x & 63, g = threadIdx.x >> 6;   // row in tile, column within the quarter
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int t = it >> 2, q = it & 3;
         int rb = 0, rem = t;
         while (rem >= colb - rb) { rem -= colb - rb; ++rb; }
         const int cb = rb + rem;
         const int row_size = min(n - rb * 64, 64), col_size = min(n - cb * 64, 64);
-        if (threadIdx.x < col_size) {
+        if (threadIdx.x < 16 && q * 16 + (int)threadIdx.x < col_size) {
 #pragma unroll
-            for (int e = 0; e < 5; ++e) s_col[threadIdx.x * 5 + e] = bx[(size_t)(cb * 64 + threadIdx.x) * 5 + e];
+            for (int e = 0; e < 5; ++e) s_col[threadIdx.x * 5 + e] = bx[(size_t)(cb * 64 + q * 16 + threadIdx.x) * 5 + e];
         }
-        if (threadIdx.x < 64) s_bits[threadIdx.x] = 0ULL;
+        if (threadIdx.x < 64) s_bits[threadIdx.x] = 0u;
         __syncthreads();
-        if (r < row_size) {
+        const int j = q * 16 + g;                            // column of the tile
+        if (r < row_size && j < col_size && !(rb == cb && j <= r)) {
             const int i = rb * 64 + r;
             float cur[5];
 #pragma unroll
             for (int e = 0; e < 5; ++e) cur[e] = bx[(size_t)i * 5 + e];
-            unsigned long long bits = 0;
-            const int start = (rb == cb) ? r + 1 : 0;
-            const int j0 = max(start, g * 4), j1 = min(col_size, g * 4 + 4);
             // Boxes whose circumscribed circles are apart cannot intersect: the reference's overlap is exactly 0
             // there and 0 > thr is false, so skipping them leaves the mask bit-identical (thr >= 0; the 1e-3 margin
-            // keeps every touching pair on the exact path).  Most of the 64x64 pairs of a tile go this way.
-            const float cx = 0.5f * (cur[0] + cur[2]), cy = 0.5f * (cur[1] + cur[3]);
-            const float rad = 0.5f * sqrtf((cur[2] - cur[0]) * (cur[2] - cur[0]) + (cur[3] - cur[1]) * (cur[3] - cur[1]));
-            for (int j = j0; j < j1; j++) {
-                const float* o = s_col + j * 5;
-                if (thr >= 0.f) {
-                    const float dx = 0.5f * (o[0] + o[2]) - cx, dy = 0.5f * (o[1] + o[3]) - cy;
-                    const float reach =
-                        rad + 0.5f * sqrtf((o[2] - o[0]) * (o[2] - o[0]) + (o[3] - o[1]) * (o[3] - o[1]));
-                    if (dx * dx + dy * dy > reach * reach * 1.002f + 1e-6f) continue;
-                }
-                if (rotated_iou(cur, o) > thr) bits |= 1ULL << j;
+            // keeps every touching pair on the exact path).  Most pairs go this way.
+            const float* o = s_col + g * 5;
+            bool far = false;
+            if (thr >= 0.f) {
+                const float cx = 0.5f * (cur[0] + cur[2]), cy = 0.5f * (cur[1] + cur[3]);
+                const float rad = 0.5f * sqrtf((cur[2] - cur[0]) * (cur[2] - cur[0]) + (cur[3] - cur[1]) * (cur[3] - cur[1]));
+                const float dx = 0.5f * (o[0] + o[2]) - cx, dy = 0.5f * (o[1] + o[3]) - cy;
+                const float reach = rad + 0.5f * sqrtf((o[2] - o[0]) * (o[2] - o[0]) + (o[3] - o[1]) * (o[3] - o[1]));
+                far = dx * dx + dy * dy > reach * reach * 1.002f + 1e-6f;
             }
-            if (bits) atomicOr(&s_bits[r], bits);
+            if (!far && rotated_iou(cur, o) > thr) atomicOr(&s_bits[r], 1u << g);
         }
         __syncthreads();
-        if (threadIdx.x < row_size)
-            mask[((size_t)f * n_cap + rb * 64 + threadIdx.x) * colb_cap + cb] = s_bits[threadIdx.x];
+        if (threadIdx.x < row_size)      // my 16-bit quarter of the (row, cb) word (little endian: half-word q)
+            ((unsigned short*)mask)[(((size_t)f * n_cap + rb * 64 + threadIdx.x) * colb_cap + cb) * 4 + q] =
+                (unsigned short)s_bits[threadIdx.x];
         __syncthreads();
     }
 }
@@ -418,8 +418,8 @@ extern "C" int sassd_nms_mask(const float* boxes5, int n, float thr, uint64_t* m
     if (n == 0) return SASSD_OK;
     const int colb = (n + 63) / 64;
     cudaMemsetAsync(mask, 0, (size_t)n * colb * 8, (cudaStream_t)stream_);
-    const long long ntiles = (long long)colb * (colb + 1) / 2;
-    dim3 grid((unsigned)(ntiles < 148 * 16 ? ntiles : 148 * 16), 1);
+    const long long nitems = 4ll * colb * (colb + 1) / 2;    // quarter tiles
+    dim3 grid((unsigned)(nitems < 148 * 16 ? nitems : 148 * 16), 1);
     nms_mask_kernel<<<grid, NMS_MASK_THREADS, 0, (cudaStream_t)stream_>>>(boxes5, nullptr, n, n, colb, thr,
                                                             (unsigned long long*)mask);
     return sassd_check_launch();

@@ -18,7 +18,7 @@ class VoxelParams(ctypes.Structure):
 
 class Conv2dDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "H", "W", "cin", "cin_stored", "cout", "taps", "relu",
-                                              "out_f32_stride", "out_split_ch", "tile_order")]
+                                              "out_f32_stride", "out_split_ch", "tile_order", "n_split")]
 
 
 class SpconvDesc(ctypes.Structure):

@@ -389,6 +389,7 @@ class SplitMap:
 
 
 TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # constant-region tile skipping in the BEV convs
+CONV2D_NSPLIT_MAX_TILES = 1184   # B <= 4 at 200x176: measured +5 % (B=1), +15 % (B=4) on `value`, nothing beyond
 CONV2D_TILE_ORDER = 0       # 1 while a latency-oriented step is captured (computed tiles first, see sassd_b200.h)
 CONV2D_COUNTERS = None     # bench instrumentation: {label: int32[2] device tensor} += tiles computed, += tiles
 _TILE_FAR = 1 << 20
@@ -457,6 +458,9 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     d.batch, d.H, d.W, d.cin, d.cin_stored = B, H, W, cin, x.planes.shape[-1]
     d.cout, d.taps, d.relu = cout, taps, 1 if relu else 0
     d.tile_order = CONV2D_TILE_ORDER
+    # latency-oriented steps split the 3x3 256-channel layers of small maps into half-width units (sassd_b200.h)
+    tiles = B * ((H + 7) // 8) * ((W + 15) // 16)
+    d.n_split = 2 if (CONV2D_TILE_ORDER and taps == 9 and cout > 128 and tiles <= CONV2D_NSPLIT_MAX_TILES) else 0
     osp = of = None
     if out_split:
         cs = (cout + 63) // 64 * 64

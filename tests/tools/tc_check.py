@@ -158,6 +158,10 @@ if stage in ("tma", "all"):
 if stage in ("tmaperf", "all"):
     run_tma(1, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=1", time_it=True)
     run_tma(4, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=4", time_it=True)
+if stage in ("tmaperf1",):
+    run_tma(1, 200, 176, 256, 256, 9, True, "tma BEV 3x3 B=1", time_it=True)
+    run_tma(1, 200, 176, 256, 256, 1, True, "tma BEV 1x1 B=1", time_it=True)
+    run_tma(4, 200, 176, 256, 256, 1, True, "tma BEV 1x1 B=4", time_it=True)
 print("done")
 if stage in ("tmafull",):
     run_tma(1, 200, 176, 256, 28, 9, True, "tma full 256->28")
