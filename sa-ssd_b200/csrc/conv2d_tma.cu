@@ -38,7 +38,7 @@ constexpr int WARP_LOAD = EPI_WARPS, WARP_ISSUE = EPI_WARPS + 1;
 
 template <int BN>
 struct Cfg2 {
-    static constexpr int B_TILE_BYTES = BN * 168;
+    static constexpr int B_TILE_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
     static constexpr int ACC_BUFS = (4 * BN <= 512) ? 2 : 1;
@@ -93,7 +93,8 @@ struct Conv2dArgs {
     int nsplit;           // work units per tile: 1, or 2 = each unit computes BN of the 2*BN output channels (the weight
                           // pack is the 2*BN-wide one; small maps, where whole tiles are too coarse to balance 148 SMs)
     int dbg;              // SASSD_TMA_DBG (timing experiments only): 1 = reuse stale B stages, 2 = reuse stale A stages,
-                          // 4 = plain MMAs (no operand collector), 8 = no TMA stores, 16 = no wait for the staging buffer
+                          // 4 = plain MMAs (no operand collector), 8 = no TMA stores, 16 = no wait for the staging buffer,
+                          // 32 = constant tiles through the staged TMA path
 };
 
 // True when tile (ty, tx) sees a constant input and its output is p.cvec (see sassd_conv2d_f16x3_occ in the header).
@@ -330,6 +331,36 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
             }
             stamp(5);
             ++store_it;
+        }
+    }
+}
+
+// A unit of a constant-region tile: every pixel gets the layer's constant vector (channels [n_off, n_off + ncols) of it).
+// No staging and no TMA: lane g of a pixel's group holds 8 channels of the split constant in registers and the EW
+// epilogue warps write whole pixels with 16-byte stores (ncols / 8 lanes cover one pixel: 512 contiguous bytes at
+// ncols = 256).  Same values, bit for bit, as drain_cols(const_tile = true).  Requires vpp = ncols / 8 in {8, 16, 32}.
+template <int EW>
+__device__ __forceinline__ void store_constant_unit(const Conv2dArgs& p, int b, int ty, int tx, int n_off, int ncols,
+                                                    int warp, int lane) {
+    const int vpp = ncols >> 3, g = lane % vpp, sub = lane / vpp, ppi = 32 / vpp;
+    const int c = n_off + 8 * g;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j) < p.cout ? __ldg(&p.cvec[c + j]) : 0.f;
+    uint4 hi, lo;
+    split_f16x2(v[0], v[1], hi.x, lo.x);
+    split_f16x2(v[2], v[3], hi.y, lo.y);
+    split_f16x2(v[4], v[5], hi.z, lo.z);
+    split_f16x2(v[6], v[7], hi.w, lo.w);
+    const size_t plane = (size_t)p.batch * p.H * p.W * p.out_split_ch;
+#pragma unroll 4
+    for (int pg = warp; pg * ppi < TILE_H * TILE_W; pg += EW) {
+        const int pix = pg * ppi + sub;
+        const int y = ty * TILE_H + pix / TILE_W, x = tx * TILE_W + pix % TILE_W;
+        if (y < p.H && x < p.W) {
+            __half* dst = p.out_split + (((size_t)b * p.H + y) * p.W + x) * p.out_split_ch + c;
+            *(uint4*)dst = hi;
+            *(uint4*)(dst + plane) = lo;
         }
     }
 }
@@ -575,8 +606,12 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             const int b = tile / (tiles_y * tiles_x);
             const int ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
             if (ref & kConstTile) {                                         // no MMAs ran for this tile
-                drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {}, true,
-                                       n_off);
+                const int ncols = min(BN, p.out_split_ch - n_off);
+                if (p.out_split && !p.out_f32 && (ncols == 64 || ncols == 128 || ncols == 256) && !(p.dbg & 32))
+                    store_constant_unit<C::EW>(p, b, ty, tx, n_off, ncols, warp, lane);
+                else
+                    drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {},
+                                           true, n_off);
                 continue;
             }
             const long long c0 = tr ? clock64() : 0;
@@ -619,7 +654,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 // the pair); tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs; the peer's epilogue
 // warps release the accumulator with a remote arrive on the leader's tmem_empty barrier.
 constexpr int STAGES_2CTA = 3;
-constexpr int B_HALF_BYTES = 128 * 168;                                   // 128 of the 256 weight rows, one plane
+constexpr int B_HALF_BYTES = 128 * 128;                                   // 128 of the 256 weight rows, one plane
 constexpr int STAGE_2CTA_BYTES = 2 * A_TILE_BYTES + 2 * B_HALF_BYTES;     // 64 KB
 constexpr int OUT_STAGE_2CTA_BYTES = EPI_WARPS * 2 * 4096;
 constexpr int SMEM_2CTA_BYTES = STAGES_2CTA * STAGE_2CTA_BYTES + OUT_STAGE_2CTA_BYTES + 1024 + 256;
@@ -750,7 +785,7 @@ conv2d_tma_pair_kernel(const __grid_constant__ CUtensorMap amap, const __grid_co
                         tma_load_4d_pair(a_hi, &amap, kc * BKC, x0 + dx, y0 + dy, b, bar);
                         tma_load_4d_pair(a_lo, &amap, kc * BKC, x0 + dx, y0 + dy, p.batch + b, bar);
                         // weight rows of this CTA's half: block (t, kc) = [hi 256 rows][lo 256 rows]
-                        const int row = (t * kchunks + kc) * 2 * BN + (int)rank * 168;
+                        const int row = (t * kchunks + kc) * 2 * BN + (int)rank * 128;
                         tma_load_2d_pair(b_hi, &bmap, 0, row, bar);
                         tma_load_2d_pair(b_lo, &bmap, 0, row + BN, bar);
                         if (++stage == STAGES_2CTA) { stage = 0; phase ^= 1u; }
