@@ -121,6 +121,14 @@ size_t sassd_rulebook_conv_workspace_bytes(int batch, int Do, int Ho, int Wo);
 int sassd_rulebook_conv_outputs(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in, int batch,
                                 int D, int H, int W, int32_t* coors_out, int32_t* d_rows_out, int rows_cap_out,
                                 int32_t* d_status, void* ws, size_t ws_bytes, sassd_stream_t stream);
+/* Same, and every output row is inserted into the hash index of the OUTPUT level as it is written (keys_out / vals_out
+ * [slots_out], slots_out a power of two >= 2 * rows_cap_out; cleared here), which replaces that level's
+ * sassd_hash_build launch.  Two kernels: mark (bitmap over the output grid) and a single-pass compaction (block scan
+ * + decoupled look-back over the chunks of the bitmap). */
+int sassd_rulebook_conv_outputs_hash(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in, int batch,
+                                     int D, int H, int W, int32_t* coors_out, int32_t* d_rows_out, int rows_cap_out,
+                                     int32_t* keys_out, int32_t* vals_out, int slots_out, int32_t* d_status, void* ws,
+                                     size_t ws_bytes, sassd_stream_t stream);
 /* neighbour table of the strided conv: nbr[o][k] = row of input cell 2*o - 1 + k. */
 int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* d_rows_out, int rows_cap_out, int D, int H, int W,
                             const int32_t* keys_in, const int32_t* vals_in, int slots_in, int32_t* nbr,

@@ -212,11 +212,17 @@ __device__ __forceinline__ void drain_tile(const Conv2dArgs& p, const CUtensorMa
     }
 }
 
-// Epilogue of the columns [col0, col0 + CPW) of one 8x16-pixel tile for the warp that owns TMEM lane quarter `quad`:
-// ALL of its accumulator columns are read into registers first (big + small/2048 combined, so CPW fp32 registers),
-// then the accumulator buffer is released to the MMA warp, and only then comes the BN / ReLU / split math and the TMA
-// stores (same arithmetic and store path as drain_tile).  double_buf: this warp owns two staging buffers.
-template <int BN, int CPW, class Release>
+// Epilogue of the columns [col0, col0 + CPW) of one 8x16-pixel tile for the warp that owns TMEM lane quarter `quad`
+// (same arithmetic and store path as drain_tile).  double_buf: this warp owns two staging buffers.
+//   ROLLED = false (BN = 256, single accumulator buffer): ALL of the warp's accumulator columns are read into registers
+//     first (big + small/2048 combined: CPW fp32 registers), the accumulator is released to the MMA warp, then the
+//     slices are processed - four unrolled copies of the slice code.
+//   ROLLED = true (double-buffered accumulators): one slice at a time in a rolled loop.  At B = 1 a CTA runs this code
+//     once or twice per launch, so it executes at instruction-fetch speed: the unrolled form's first pass cost 19-25k
+//     clk against 6.5k for a warm one (profiles/r2_dense_epilogue.md).
+// BN scale / shift: lane l holds column c0 + l of the slice (two loads per slice, issued before the TMEM loads) and
+// the FMAs take them by shuffle - instead of 16 broadcast float4 loads per slice in the dependent chain.
+template <int BN, int CPW, bool ROLLED, class Release>
 __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMap* omap, uint32_t tmem_acc, int quad,
                                            int col0, int lane, int b, int ty, int tx, uint32_t my_stage, bool double_buf,
                                            uint32_t& store_it, Release&& release, bool const_tile, int n_off = 0,
@@ -227,68 +233,30 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
     const bool valid = y < p.H && x < p.W;
     const size_t pix = ((size_t)b * p.H + y) * p.W + x;
     const uint32_t row_off = (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
-    const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
-    constexpr int CW = 32;
-    float acc[CPW];
+    constexpr int CW = 32, NS = CPW / CW;
     long long tq = ph ? clock64() : 0;
     auto stamp = [&](int i) { if (ph) { const long long t = clock64(); ph[i] += t - tq; tq = t; } };
-    if (!const_tile) {
-#pragma unroll
-        for (int s0 = 0; s0 < CPW; s0 += CW) {
-            uint32_t v[CW], u[CW];
-            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(col0 + s0);
-            tmem_ld<CW>(v, taddr);
-            tmem_ld<CW>(u, taddr + (uint32_t)BN);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < CW; ++j)
-                acc[s0 + j] = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]) * (1.f / kF16LoScale));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release();           // accumulators are in registers: the next tile's MMAs may start
-    }
-    stamp(0);
-#pragma unroll
-    for (int s0 = 0; s0 < CPW; s0 += CW) {
-        const int c0 = n_off + col0 + s0;       // output channel of this slice's first column
+    const uint32_t tbase = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+    // this lane's column of slice s: folded-BN scale and shift (1, 0 beyond cout: those accumulators are exact zeros)
+    auto lane_scale = [&](int s) { const int n = n_off + col0 + s * CW + lane; return (p.scale && n < p.cout) ? __ldg(&p.scale[n]) : 1.f; };
+    auto lane_shift = [&](int s) { const int n = n_off + col0 + s * CW + lane; return (p.shift && n < p.cout) ? __ldg(&p.shift[n]) : 0.f; };
+    // one 32-column slice: BN + ReLU (or the layer constant), fp32 store and / or split -> staging -> TMA store
+    auto emit = [&](const float (&a)[CW], float scl, float shl, int s) {
+        const int c0 = n_off + col0 + s * CW;       // output channel of this slice's first column
         float o[CW];
         if (const_tile) {         // constant input region: the output is the layer's precomputed constant vector
+            const float cv = (c0 + lane) < p.cout ? __ldg(&p.cvec[c0 + lane]) : 0.f;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) o[j] = (c0 + j) < p.cout ? __ldg(&p.cvec[c0 + j]) : 0.f;
+            for (int j = 0; j < CW; ++j) o[j] = __shfl_sync(0xffffffffu, cv, j);
         } else {
 #pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-                const int n = c0 + j;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (vec_ss) {
-                    if (n < p.cout) {
-                        sc = __ldg((const float4*)(p.scale + n));
-                        sh = __ldg((const float4*)(p.shift + n));
-                    }
-                } else {
-                    if (p.scale) {
-                        if (n + 0 < p.cout) sc.x = __ldg(&p.scale[n + 0]);
-                        if (n + 1 < p.cout) sc.y = __ldg(&p.scale[n + 1]);
-                        if (n + 2 < p.cout) sc.z = __ldg(&p.scale[n + 2]);
-                        if (n + 3 < p.cout) sc.w = __ldg(&p.scale[n + 3]);
-                    }
-                    if (p.shift) {
-                        if (n + 0 < p.cout) sh.x = __ldg(&p.shift[n + 0]);
-                        if (n + 1 < p.cout) sh.y = __ldg(&p.shift[n + 1]);
-                        if (n + 2 < p.cout) sh.z = __ldg(&p.shift[n + 2]);
-                        if (n + 3 < p.cout) sh.w = __ldg(&p.shift[n + 3]);
-                    }
-                }
-                const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float val = fmaf(acc[s0 + j + e], scs[e], shs[e]);
-                    if (p.relu) val = fmaxf(val, 0.f);
-                    o[j + e] = (n + e) < p.cout ? val : 0.f;
-                }
+            for (int j = 0; j < CW; ++j) {
+                float val = fmaf(a[j], __shfl_sync(0xffffffffu, scl, j), __shfl_sync(0xffffffffu, shl, j));
+                if (p.relu) val = fmaxf(val, 0.f);
+                o[j] = val;
             }
         }
+        stamp(1);
         if (p.out_f32 && valid) {
             float* orow = p.out_f32 + pix * p.out_f32_stride;
 #pragma unroll
@@ -300,7 +268,6 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
                         if (n + e < p.out_f32_stride) orow[n + e] = o[j + e];
             }
         }
-        stamp(1);
         if (p.out_split && c0 < p.out_split_ch) {
             const uint32_t buf = my_stage + (double_buf ? (store_it & 1u) * 4096u : 0u);
             if (store_it >= (double_buf ? 2u : 1u) && !(p.dbg & 16)) {   // the store that last used this buffer has read it
@@ -332,6 +299,46 @@ __device__ __forceinline__ void drain_cols(const Conv2dArgs& p, const CUtensorMa
             stamp(5);
             ++store_it;
         }
+    };
+    auto load_slice = [&](float (&a)[CW], int s) {      // big + small / 2048 of 32 accumulator columns
+        uint32_t v[CW], u[CW];
+        tmem_ld<CW>(v, tbase + (uint32_t)(s * CW));
+        tmem_ld<CW>(u, tbase + (uint32_t)(s * CW) + (uint32_t)BN);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < CW; ++j) a[j] = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(u[j]) * (1.f / kF16LoScale));
+    };
+    if constexpr (ROLLED) {
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+            float a[CW];
+            float scl = 1.f, shl = 0.f;
+            if (!const_tile) {
+                scl = lane_scale(s); shl = lane_shift(s);
+                load_slice(a, s);
+                if (s == NS - 1) {          // the last columns are in registers: the MMA warp may reuse this buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) release();
+                }
+            }
+            stamp(0);
+            emit(a, scl, shl, s);
+        }
+    } else {
+        float acc[NS][CW], scl[NS], shl[NS];
+        if (!const_tile) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) { scl[s] = lane_scale(s); shl[s] = lane_shift(s); }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) load_slice(acc[s], s);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release();           // accumulators are in registers: the next tile's MMAs may start
+        }
+        stamp(0);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) emit(acc[s], scl[s], shl[s], s);
     }
 }
 
@@ -423,24 +430,25 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     // instead of one per tile and role) and keeps the verdicts as order[k] bit 15.
     if (small_map) {
         if (warp == 0) {
-            constexpr int PER = (C::ORDER_CAP + 31) / 32;
-            int dist[PER];
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int t = i * 32 + lane;
-                dist[i] = t < ntiles ? __ldg(&p.tile_dist[t]) : 0;
-            }
+            // verdicts of tiles lane, lane + 32, ... as bits of one word; the distances are fetched four at a time
+            // (rolled: at B = 1 this code runs once per launch, at instruction-fetch speed)
             uint32_t cst_bits = 0u;
+            int ty = (lane / tiles_x) % tiles_y, tx = lane % tiles_x;      // tile `lane`; advanced by 32 tiles per slot
+#pragma unroll 1
+            for (int i0 = 0; i0 * 32 < ntiles; i0 += 4) {
+                int dist[4];
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                if (i * 32 < ntiles) {                                   // warp-uniform
-                    const int t = i * 32 + lane;
-                    bool cst = t < ntiles && dist[i] > p.reach;
-                    if (cst && p.reach >= 2) {                           // border tiles see the zero padding
-                        const int ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
-                        cst = !(ty == 0 || ty == tiles_y - 1 || tx == 0 || tx == tiles_x - 1);
-                    }
-                    if (cst) cst_bits |= 1u << i;
+                for (int e = 0; e < 4; ++e) {
+                    const int t = (i0 + e) * 32 + lane;
+                    dist[e] = t < ntiles ? __ldg(&p.tile_dist[t]) : 0;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int t = (i0 + e) * 32 + lane;
+                    const bool border = ty == 0 || ty == tiles_y - 1 || tx == 0 || tx == tiles_x - 1;   // sees the zero padding
+                    if (t < ntiles && dist[e] > p.reach && (p.reach < 2 || !border)) cst_bits |= 1u << (i0 + e);
+                    tx += 32;
+                    while (tx >= tiles_x) { tx -= tiles_x; if (++ty == tiles_y) ty = 0; }
                 }
             }
             if (use_order) {
@@ -610,7 +618,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 if (p.out_split && !p.out_f32 && (ncols == 64 || ncols == 128 || ncols == 256) && !(p.dbg & 32))
                     store_constant_unit<C::EW>(p, b, ty, tx, n_off, ncols, warp, lane);
                 else
-                    drain_cols<BN, C::CPW>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {},
+                    drain_cols<BN, C::CPW, (C::ACC_BUFS == 2)>(p, &omap, 0u, quad, col0, lane, b, ty, tx, my_stage, kDoubleBuf, store_it, [] {},
                                            true, n_off);
                 continue;
             }
@@ -620,7 +628,7 @@ conv2d_tma_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             tc_fence_after();
             const long long c1 = tr ? clock64() : 0;
             const uint32_t bar = tmem_empty(acc);
-            drain_cols<BN, C::CPW>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), quad, col0, lane, b, ty, tx, my_stage,
+            drain_cols<BN, C::CPW, (C::ACC_BUFS == 2)>(p, &omap, tmem_base + (uint32_t)(acc * 2 * BN), quad, col0, lane, b, ty, tx, my_stage,
                                    kDoubleBuf, store_it, [bar] { mbar_arrive(bar); }, false, n_off, tr ? phase_clk : nullptr);
             if (tr) { e_wait += c1 - c0; e_drain += clock64() - c1; }
             if (++acc == C::ACC_BUFS) { acc = 0; acc_phase ^= 1u; }

@@ -147,7 +147,7 @@ extern "C" int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* 
 // ---------------------------------------------------------------------------
 // strided conv output set (k=3, s=2, p=1)
 // ---------------------------------------------------------------------------
-#define BM_CHUNK 1024  // bitmap words per scan chunk
+#define BM_CHUNK 2048  // bitmap words per CTA of the compaction pass (512 threads x 4 consecutive words)
 
 // Warp-aggregated marking: a warp covers 4 input rows x 8 candidate outputs; neighbouring inputs feed the same
 // output cells, so lanes that hit the same bitmap word find each other (__match_any_sync), OR their bits in the warp
@@ -195,71 +195,100 @@ conv_mark_kernel(const int4* __restrict__ coors_in, const int* __restrict__ d_ro
     }
 }
 
-__global__ void __launch_bounds__(256)
-bm_count_kernel(const uint32_t* __restrict__ bitmap, int nwords, int* __restrict__ chunk_count) {
-    __shared__ int s_red[8];
+// Bitmap -> sorted output rows in ONE pass (round 1: count / scan / emit, three launches on the rulebook chain's
+// critical path).  A CTA owns BM_CHUNK consecutive bitmap words, four consecutive words per thread, so one block scan
+// over the per-thread popcounts orders the rows by ascending cell index.  The chunk totals are chained by decoupled
+// look-back: a CTA publishes {AGGREGATE, total}, walks back over its predecessors' descriptors until it meets an
+// inclusive prefix and then publishes its own (CTAs are dispatched in index order, so the ones it waits for are
+// running or done).  Each row is written and, when the caller passes the next level's hash table (keys pre-filled
+// with SASSD_EMPTY_KEY), inserted into it on the spot - the separate sassd_hash_build launch of that level goes away.
+#define BM_FLAG_AGG 1ull
+#define BM_FLAG_PREFIX 2ull
+__global__ void __launch_bounds__(BM_CHUNK / 4)
+bm_compact_kernel(const uint4* __restrict__ bitmap4, int nwords, unsigned long long* __restrict__ desc, int nchunks,
+                  int Do, int Ho, int Wo, int rows_cap, int4* __restrict__ coors_out, int* __restrict__ d_rows_out,
+                  int* __restrict__ keys, int* __restrict__ vals, int slots, int* __restrict__ status) {
+    __shared__ int s_scan[33];
+    __shared__ int s_base;
     const int c = blockIdx.x;
-    int acc = 0;
-    for (int w = threadIdx.x; w < BM_CHUNK; w += 256) {
-        const int idx = c * BM_CHUNK + w;
-        if (idx < nwords) acc += __popc(bitmap[idx]);
-    }
+    const int w0 = c * BM_CHUNK + 4 * (int)threadIdx.x;          // my four consecutive words (nwords is padded to 4)
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (w0 < nwords) q = __ldg(&bitmap4[w0 >> 2]);
+    uint32_t bits[4] = {q.x, q.y, q.z, q.w};
+    const int mine = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+    int total;
+    const int ex = sassd_block_exscan(mine, s_scan, &total);
+    if (threadIdx.x < 32) {            // warp 0: publish, look back 32 predecessors at a time, publish the prefix
+        volatile unsigned long long* vd = desc;
+        const int lane = threadIdx.x;
+        int base = 0;
+        if (c > 0) {
+            if (lane == 0) vd[c] = (BM_FLAG_AGG << 32) | (unsigned)total;
+            for (int j0 = c - 1; j0 >= 0; j0 -= 32) {
+                const int j = j0 - lane;
+                unsigned long long d = BM_FLAG_PREFIX << 32;            // lanes before chunk 0: an empty prefix
+                if (j >= 0) do { d = vd[j]; } while ((d >> 32) == 0ull);
+                const unsigned pref = __ballot_sync(0xffffffffu, (d >> 32) == BM_FLAG_PREFIX);
+                const int first = __ffs(pref) - 1;                     // nearest predecessor with an inclusive prefix
+                int v = (pref == 0u || lane <= first) ? (int)(unsigned)d : 0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < 8; ++i) t += s_red[i];
-        chunk_count[c] = t;
-    }
-}
-
-// single CTA: exclusive scan of the chunk counts, total -> d_rows_out
-__global__ void __launch_bounds__(1024)
-bm_scan_kernel(int* __restrict__ chunk_count, int nchunks, int rows_cap, int* __restrict__ d_rows_out,
-               int* __restrict__ status) {
-    __shared__ int s_scan[33];
-    int base = 0;
-    for (int c0 = 0; c0 < nchunks; c0 += 1024) {
-        const int c = c0 + threadIdx.x;
-        const int v = c < nchunks ? chunk_count[c] : 0;
-        int total;
-        const int ex = sassd_block_exscan(v, s_scan, &total);
-        if (c < nchunks) chunk_count[c] = base + ex;
-        base += total;
-    }
-    if (threadIdx.x == 0) {
-        if (base > rows_cap) { atomicOr(status, SASSD_FLAG_ROWS_CAP); base = rows_cap; }
-        *d_rows_out = base;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-bm_emit_kernel(const uint32_t* __restrict__ bitmap, int nwords, const int* __restrict__ chunk_off, int Do, int Ho,
-               int Wo, int rows_cap, int4* __restrict__ coors_out) {
-    __shared__ int s_scan[33];
-    const int c = blockIdx.x;
-    int base = chunk_off[c];
-    // 4 rounds of 256 consecutive words keep the output order = ascending cell index
-    for (int w0 = 0; w0 < BM_CHUNK; w0 += 256) {
-        const int idx = c * BM_CHUNK + w0 + threadIdx.x;
-        uint32_t bits = idx < nwords ? bitmap[idx] : 0u;
-        int total;
-        int row = base + sassd_block_exscan(__popc(bits), s_scan, &total);
-        while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (row < rows_cap) {
-                int cell = idx * 32 + bit;
-                const int x = cell % Wo; cell /= Wo;
-                const int y = cell % Ho; cell /= Ho;
-                const int z = cell % Do; cell /= Do;
-                coors_out[row] = make_int4(cell, z, y, x);
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base += v;
+                if (pref) break;
             }
-            ++row;
         }
-        base += total;
+        if (lane == 0) {
+            vd[c] = (BM_FLAG_PREFIX << 32) | (unsigned)(base + total);
+            s_base = base;
+            if (c == nchunks - 1) {
+                int all = base + total;
+                if (all > rows_cap) { atomicOr(status, SASSD_FLAG_ROWS_CAP); all = rows_cap; }
+                *d_rows_out = all;
+            }
+        }
+    }
+    __syncthreads();
+    const int base_row = s_base;
+    if (mine) {
+        int row = base_row + ex;
+        // (b, z, y, x) of the first cell of my first word; then walk with carries (no division per row)
+        int cell0 = w0 * 32;
+        int x = cell0 % Wo; cell0 /= Wo;
+        int y = cell0 % Ho; cell0 /= Ho;
+        int z = cell0 % Do;
+        int b = cell0 / Do;
+        int at = 0;                                              // cells advanced since (b, z, y, x) was computed
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t m = bits[i];
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int tgt = i * 32 + bit;
+                x += tgt - at; at = tgt;
+                while (x >= Wo) { x -= Wo; if (++y == Ho) { y = 0; if (++z == Do) { z = 0; ++b; } } }
+                if (row < rows_cap) coors_out[row] = make_int4(b, z, y, x);
+                ++row;
+            }
+        }
+    }
+    if (!keys) return;
+    // Hash the chunk's rows with the whole CTA, one row per thread and round: an insertion is a chain of dependent L2
+    // atomics, so the thread that owns 128 consecutive cells must not do its (up to dozens of) rows one after the other.
+    __syncthreads();                                             // the rows above are visible to the CTA
+    const uint32_t mask = (uint32_t)slots - 1u;
+    const int nrows = min(total, max(rows_cap - base_row, 0));
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+        const int row = base_row + i;
+        const int4 cc = coors_out[row];
+        const int key = flat_key(cc.x, cc.y, cc.z, cc.w, Do, Ho, Wo);      // unique: one row per marked cell
+        uint32_t sl = sassd_hash32((uint32_t)key) & mask;
+        int probes = 0;
+        while (atomicCAS(&keys[sl], SASSD_EMPTY_KEY, key) != SASSD_EMPTY_KEY) {
+            sl = (sl + 1) & mask;
+            if (++probes >= slots) { atomicOr(status, SASSD_FLAG_HASH_FULL); break; }
+        }
+        if (probes < slots) vals[sl] = row;
     }
 }
 
@@ -267,32 +296,44 @@ static inline size_t rb_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t sassd_rulebook_conv_workspace_bytes(int batch, int Do, int Ho, int Wo) {
     const long long cells = (long long)batch * Do * Ho * Wo;
-    const long long nwords = (cells + 31) / 32;
+    const long long nwords = ((cells + 31) / 32 + 3) & ~3LL;
     const long long nchunks = (nwords + BM_CHUNK - 1) / BM_CHUNK;
-    return rb_align((size_t)nwords * 4) + rb_align((size_t)nchunks * 4);
+    return rb_align((size_t)nwords * 4) + rb_align((size_t)nchunks * 8);
+}
+
+extern "C" int sassd_rulebook_conv_outputs_hash(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in,
+                                                int batch, int D, int H, int W, int32_t* coors_out,
+                                                int32_t* d_rows_out, int rows_cap_out, int32_t* keys_out,
+                                                int32_t* vals_out, int slots_out, int32_t* d_status, void* ws,
+                                                size_t ws_bytes, sassd_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!coors_in || !d_rows_in || !coors_out || !d_rows_out || !d_status || !ws) return SASSD_ERR_ARG;
+    if (keys_out && (!vals_out || slots_out < 2 || (slots_out & (slots_out - 1)) || slots_out < 2 * rows_cap_out))
+        return SASSD_ERR_ARG;
+    const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long cells = (long long)batch * Do * Ho * Wo;
+    if (cells >= 2147483647LL - 128) return SASSD_ERR_UNSUPPORTED;
+    if (ws_bytes < sassd_rulebook_conv_workspace_bytes(batch, Do, Ho, Wo)) return SASSD_ERR_WORKSPACE;
+    const int nwords = (int)(((cells + 31) / 32 + 3) & ~3LL);
+    const int nchunks = (nwords + BM_CHUNK - 1) / BM_CHUNK;
+    uint32_t* bitmap = (uint32_t*)ws;
+    unsigned long long* desc = (unsigned long long*)((char*)ws + rb_align((size_t)nwords * 4));
+    // one memset clears the bitmap and the chunk descriptors behind it
+    cudaMemsetAsync(ws, 0, rb_align((size_t)nwords * 4) + (size_t)nchunks * 8, stream);
+    if (keys_out) cudaMemsetAsync(keys_out, 0xff, (size_t)slots_out * sizeof(int), stream);
+    conv_mark_kernel<<<sassd_grid((long long)(rows_cap_in > 0 ? rows_cap_in : 1) * 8, 256), 256, 0, stream>>>(
+        (const int4*)coors_in, d_rows_in, rows_cap_in, Do, Ho, Wo, bitmap);
+    bm_compact_kernel<<<nchunks, BM_CHUNK / 4, 0, stream>>>((const uint4*)bitmap, nwords, desc, nchunks, Do, Ho, Wo, rows_cap_out,
+                                                   (int4*)coors_out, d_rows_out, keys_out, vals_out, slots_out, d_status);
+    return sassd_check_launch();
 }
 
 extern "C" int sassd_rulebook_conv_outputs(const int32_t* coors_in, const int32_t* d_rows_in, int rows_cap_in,
                                            int batch, int D, int H, int W, int32_t* coors_out, int32_t* d_rows_out,
                                            int rows_cap_out, int32_t* d_status, void* ws, size_t ws_bytes,
                                            sassd_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!coors_in || !d_rows_in || !coors_out || !d_rows_out || !d_status || !ws) return SASSD_ERR_ARG;
-    const int Do = (D + 2 - 3) / 2 + 1, Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const long long cells = (long long)batch * Do * Ho * Wo;
-    if (cells >= 2147483647LL) return SASSD_ERR_UNSUPPORTED;
-    if (ws_bytes < sassd_rulebook_conv_workspace_bytes(batch, Do, Ho, Wo)) return SASSD_ERR_WORKSPACE;
-    const int nwords = (int)((cells + 31) / 32);
-    const int nchunks = (nwords + BM_CHUNK - 1) / BM_CHUNK;
-    uint32_t* bitmap = (uint32_t*)ws;
-    int* chunk = (int*)((char*)ws + rb_align((size_t)nwords * 4));
-    cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4, stream);
-    conv_mark_kernel<<<sassd_grid((long long)(rows_cap_in > 0 ? rows_cap_in : 1) * 8, 256), 256, 0, stream>>>(
-        (const int4*)coors_in, d_rows_in, rows_cap_in, Do, Ho, Wo, bitmap);
-    bm_count_kernel<<<nchunks, 256, 0, stream>>>(bitmap, nwords, chunk);
-    bm_scan_kernel<<<1, 1024, 0, stream>>>(chunk, nchunks, rows_cap_out, d_rows_out, d_status);
-    bm_emit_kernel<<<nchunks, 256, 0, stream>>>(bitmap, nwords, chunk, Do, Ho, Wo, rows_cap_out, (int4*)coors_out);
-    return sassd_check_launch();
+    return sassd_rulebook_conv_outputs_hash(coors_in, d_rows_in, rows_cap_in, batch, D, H, W, coors_out, d_rows_out,
+                                            rows_cap_out, nullptr, nullptr, 0, d_status, ws, ws_bytes, stream_);
 }
 
 // ---------------------------------------------------------------------------

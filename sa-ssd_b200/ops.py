@@ -51,7 +51,7 @@ def next_pow2(n):
 # --- launch accounting / optional per-call CUDA-event timing (bench.py) ---------------
 # kernels launched by each C-ABI entry point (memsets not counted)
 _KERNELS = {"sassd_voxelize": 4, "sassd_voxel_mean": 1, "sassd_anchor_mask": 4, "sassd_hash_build": 1,
-            "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 4, "sassd_rulebook_conv_nbr": 1,
+            "sassd_rulebook_subm": 1, "sassd_rulebook_conv_outputs": 2, "sassd_rulebook_conv_outputs_hash": 2, "sassd_rulebook_conv_nbr": 1,
             "sassd_rulebook_pairs": 1, "sassd_gconv": 1, "sassd_gconv_pack": 1, "sassd_spconv_pack": 1, "sassd_rotate_overlap_eval": 1, "sassd_conv2d_f16x3": 1, "sassd_conv2d_f16x3_occ": 1, "sassd_spconv_f16x3": 1, "sassd_features_to_split": 1, "sassd_split_rows_to_bev": 1, "sassd_sparse_to_bev_split": 1, "sassd_sparse_to_bev": 1, "sassd_decode_select": 2,
             "sassd_pswarp": 1, "sassd_rescore_nms": 3, "sassd_nms_mask": 1, "sassd_nms_sorted": 2,
             "sassd_boxes_iou_bev": 1}
@@ -177,23 +177,46 @@ def conv_out_shape(shape):
     return [(s + 2 - 3) // 2 + 1 for s in shape]
 
 
-def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, status, ws=None, ws_key="rbconv"):
-    """Strided (k3,s2,p1) rulebook.  Returns coors_out [cap,4], d_rows_out [1], nbr [cap,27], out_shape, tile_mask."""
+def rulebook_conv_outputs(coors_in, d_rows_in, batch, shape, rows_cap_out, status, ws=None, ws_key="rbconv",
+                          index_out=None):
+    """Active output set of a strided (k3,s2,p1) conv, sorted by flattened index.  With ``index_out`` (a fresh
+    HashIndex of the output level) the rows are hashed as they are emitted.  Returns coors_out [cap,4], d_rows_out [1],
+    out_shape."""
     dev = coors_in.device
     D, H, W = shape
     Do, Ho, Wo = conv_out_shape(shape)
     coors_out = torch.empty((rows_cap_out, 4), dtype=torch.int32, device=dev)
     d_rows_out = torch.empty((1,), dtype=torch.int32, device=dev)
-    nbr = torch.empty((rows_cap_out, 27), dtype=torch.int32, device=dev)
     nbytes = _L().sassd_rulebook_conv_workspace_bytes(batch, Do, Ho, Wo)
     w = (ws or _WS).get(ws_key, nbytes, dev)
-    _call("sassd_rulebook_conv_outputs", None, _ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
-                                           _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(status), _ptr(w),
-                                           w.numel(), _stream())
-    tmask = _tile_mask_buffer(rows_cap_out, dev)
+    if index_out is None:
+        _call("sassd_rulebook_conv_outputs", None, _ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
+              _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(status), _ptr(w), w.numel(), _stream())
+    else:
+        _call("sassd_rulebook_conv_outputs_hash", None, _ptr(coors_in), _ptr(d_rows_in), coors_in.shape[0], batch, D, H, W,
+              _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, _ptr(index_out.keys), _ptr(index_out.vals),
+              index_out.slots, _ptr(status), _ptr(w), w.numel(), _stream())
+    return coors_out, d_rows_out, [Do, Ho, Wo]
+
+
+def rulebook_conv_nbr(coors_out, d_rows_out, shape_in, index_in):
+    """Neighbour table of the strided conv (probes the INPUT level's hash).  Returns nbr [cap,27], tile_mask."""
+    D, H, W = shape_in
+    rows_cap_out = coors_out.shape[0]
+    nbr = torch.empty((rows_cap_out, 27), dtype=torch.int32, device=coors_out.device)
+    tmask = _tile_mask_buffer(rows_cap_out, coors_out.device)
     _call("sassd_rulebook_conv_nbr", None, _ptr(coors_out), _ptr(d_rows_out), rows_cap_out, D, H, W, _ptr(index_in.keys),
-                                       _ptr(index_in.vals), index_in.slots, _ptr(nbr), _ptr(tmask), _stream())
-    return coors_out, d_rows_out, nbr, [Do, Ho, Wo], tmask
+          _ptr(index_in.vals), index_in.slots, _ptr(nbr), _ptr(tmask), _stream())
+    return nbr, tmask
+
+
+def rulebook_conv(coors_in, d_rows_in, batch, shape, index_in, rows_cap_out, status, ws=None, ws_key="rbconv",
+                  index_out=None):
+    """Strided (k3,s2,p1) rulebook.  Returns coors_out [cap,4], d_rows_out [1], nbr [cap,27], out_shape, tile_mask."""
+    coors_out, d_rows_out, so = rulebook_conv_outputs(coors_in, d_rows_in, batch, shape, rows_cap_out, status, ws, ws_key,
+                                                      index_out)
+    nbr, tmask = rulebook_conv_nbr(coors_out, d_rows_out, shape, index_in)
+    return coors_out, d_rows_out, nbr, so, tmask
 
 
 def rulebook_pairs(nbr, d_rows):
@@ -389,6 +412,7 @@ class SplitMap:
 
 
 TILE_OCCUPANCY = os.environ.get("SASSD_TMA_OCC", "1") != "0"     # constant-region tile skipping in the BEV convs
+CONV2D_NSPLIT_MAX_TILES_STREAM = int(os.environ.get("SASSD_NSPLIT_STREAM_TILES", "296"))   # detect_stream slots: B = 1 only (+3 % e2e)
 CONV2D_NSPLIT_MAX_TILES = 1184   # B <= 4 at 200x176: measured +5 % (B=1), +15 % (B=4) on `value`, nothing beyond
 CONV2D_TILE_ORDER = 0       # 1 while a latency-oriented step is captured (computed tiles first, see sassd_b200.h)
 CONV2D_COUNTERS = None     # bench instrumentation: {label: int32[2] device tensor} += tiles computed, += tiles
@@ -460,7 +484,7 @@ def conv2d_split(x, weight, scale, shift, relu, cout, out_split=True, out_f32=Fa
     d.tile_order = CONV2D_TILE_ORDER
     # latency-oriented steps split the 3x3 256-channel layers of small maps into half-width units (sassd_b200.h)
     tiles = B * ((H + 7) // 8) * ((W + 15) // 16)
-    d.n_split = 2 if (CONV2D_TILE_ORDER and taps == 9 and cout > 128 and tiles <= CONV2D_NSPLIT_MAX_TILES) else 0
+    d.n_split = 2 if (taps == 9 and cout > 128 and tiles <= (CONV2D_NSPLIT_MAX_TILES if CONV2D_TILE_ORDER else CONV2D_NSPLIT_MAX_TILES_STREAM)) else 0
     osp = of = None
     if out_split:
         cs = (cout + 63) // 64 * 64
