@@ -231,7 +231,10 @@ def algorithmic_work(aux, batch):
 
 # DRAM bytes of one B=1 launch of the roofline kernel with the constant-region tile skipping ON, from the committed
 # `ncu --set full` capture profiles/r2_ncu_full_conv2d_tma.md (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_DRAM_BYTES_PER_LAUNCH = {}
+NCU_DRAM_BYTES_PER_LAUNCH = {      # launch 3 of the capture: 22 799 104 B read + 748 544 B written (cold L2, B=1)
+    "tma::conv2d_tma_kernel<128> (half-width units)": 23547648,
+    "tma::conv2d_tma_kernel<256>": 23547648,      # same layer, same tiles; not captured separately at N = 256
+}
 
 
 def profile_step(model, points, pt_off, batch, maxpts, iters=3):
@@ -496,7 +499,8 @@ def run_ours(args, rank, world, local):
                         bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
                         traffic=(ncu_b1 * B) if ncu_b1 else None,
                         traffic_unit="bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the B=1 launch "
-                                     "(tile skipping on) in profiles/r2_ncu_full_conv2d_tma.md, scaled by the batch",
+                                     "(conv2d_tma_kernel<128>, tile skipping on, cold L2) in "
+                                     "profiles/r2_ncu_full_conv2d_tma.md, scaled by the batch",
                         tiles_computed=tc[0] if tc else None, tiles_total=tc[1] if tc else None,
                         tiles_computed_frac=tiles_frac,
                         peak_source="%s bf16 dense, sustained" % peaks["source"],

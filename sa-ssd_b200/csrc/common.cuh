@@ -41,6 +41,28 @@ __device__ __forceinline__ void sassd_mark_conv2d_tiles(int* __restrict__ tile_d
         }
 }
 
+// Decoupled look-back for single-pass scans over chunks: a chunk's descriptor is {flag << 32 | value}, flag 0 = not
+// published yet, AGG = the chunk's own total, PREFIX = inclusive prefix up to and including the chunk.
+#define SASSD_SCAN_AGG 1ull
+#define SASSD_SCAN_PREFIX 2ull
+// warp-wide look-back over the descriptors of chunks c-1, c-2, ...: returns the exclusive prefix of chunk c
+__device__ __forceinline__ int sassd_lookback(volatile unsigned long long* vd, int c, int lane) {
+    int base = 0;
+    for (int j0 = c - 1; j0 >= 0; j0 -= 32) {
+        const int j = j0 - lane;
+        unsigned long long d = SASSD_SCAN_PREFIX << 32;            // lanes before chunk 0: an empty prefix
+        if (j >= 0) do { d = vd[j]; } while ((d >> 32) == 0ull);
+        const unsigned pref = __ballot_sync(0xffffffffu, (d >> 32) == SASSD_SCAN_PREFIX);
+        const int first = __ffs(pref) - 1;                     // nearest predecessor with an inclusive prefix
+        int v = (pref == 0u || lane <= first) ? (int)(unsigned)d : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        base += v;
+        if (pref) break;
+    }
+    return base;
+}
+
 __device__ __forceinline__ uint32_t sassd_hash32(uint32_t k) {
     // Fibonacci hashing followed by a xor-fold; table sizes are powers of two.
     k *= 0x9E3779B1u;

@@ -147,7 +147,7 @@ extern "C" int sassd_rulebook_conv_nbr(const int32_t* coors_out, const int32_t* 
 // ---------------------------------------------------------------------------
 // strided conv output set (k=3, s=2, p=1)
 // ---------------------------------------------------------------------------
-#define BM_CHUNK 2048  // bitmap words per CTA of the compaction pass (512 threads x 4 consecutive words)
+#define BM_CHUNK 1024  // bitmap words per CTA of the compaction pass (one word per thread)
 
 // Warp-aggregated marking: a warp covers 4 input rows x 8 candidate outputs; neighbouring inputs feed the same
 // output cells, so lanes that hit the same bitmap word find each other (__match_any_sync), OR their bits in the warp
@@ -196,49 +196,32 @@ conv_mark_kernel(const int4* __restrict__ coors_in, const int* __restrict__ d_ro
 }
 
 // Bitmap -> sorted output rows in ONE pass (round 1: count / scan / emit, three launches on the rulebook chain's
-// critical path).  A CTA owns BM_CHUNK consecutive bitmap words, four consecutive words per thread, so one block scan
-// over the per-thread popcounts orders the rows by ascending cell index.  The chunk totals are chained by decoupled
+// critical path).  A CTA owns BM_CHUNK consecutive bitmap words, one per thread, so one block scan over the popcounts
+// orders the rows by ascending cell index.  The chunk totals are chained by decoupled
 // look-back: a CTA publishes {AGGREGATE, total}, walks back over its predecessors' descriptors until it meets an
 // inclusive prefix and then publishes its own (CTAs are dispatched in index order, so the ones it waits for are
 // running or done).  Each row is written and, when the caller passes the next level's hash table (keys pre-filled
 // with SASSD_EMPTY_KEY), inserted into it on the spot - the separate sassd_hash_build launch of that level goes away.
-#define BM_FLAG_AGG 1ull
-#define BM_FLAG_PREFIX 2ull
-__global__ void __launch_bounds__(BM_CHUNK / 4)
-bm_compact_kernel(const uint4* __restrict__ bitmap4, int nwords, unsigned long long* __restrict__ desc, int nchunks,
+// One bitmap word per thread: the thread that owns a solid run of cells emits at most 32 rows (with four words per
+// thread a single thread wrote up to 128 rows one after the other while its CTA waited: 26 us per launch at B=1).
+__global__ void __launch_bounds__(BM_CHUNK)
+bm_compact_kernel(const uint32_t* __restrict__ bitmap, int nwords, unsigned long long* __restrict__ desc, int nchunks,
                   int Do, int Ho, int Wo, int rows_cap, int4* __restrict__ coors_out, int* __restrict__ d_rows_out,
                   int* __restrict__ keys, int* __restrict__ vals, int slots, int* __restrict__ status) {
     __shared__ int s_scan[33];
     __shared__ int s_base;
     const int c = blockIdx.x;
-    const int w0 = c * BM_CHUNK + 4 * (int)threadIdx.x;          // my four consecutive words (nwords is padded to 4)
-    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-    if (w0 < nwords) q = __ldg(&bitmap4[w0 >> 2]);
-    uint32_t bits[4] = {q.x, q.y, q.z, q.w};
-    const int mine = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+    const int w = c * BM_CHUNK + (int)threadIdx.x;
+    uint32_t m = w < nwords ? __ldg(&bitmap[w]) : 0u;
     int total;
-    const int ex = sassd_block_exscan(mine, s_scan, &total);
+    const int ex = sassd_block_exscan(__popc(m), s_scan, &total);
     if (threadIdx.x < 32) {            // warp 0: publish, look back 32 predecessors at a time, publish the prefix
         volatile unsigned long long* vd = desc;
         const int lane = threadIdx.x;
-        int base = 0;
-        if (c > 0) {
-            if (lane == 0) vd[c] = (BM_FLAG_AGG << 32) | (unsigned)total;
-            for (int j0 = c - 1; j0 >= 0; j0 -= 32) {
-                const int j = j0 - lane;
-                unsigned long long d = BM_FLAG_PREFIX << 32;            // lanes before chunk 0: an empty prefix
-                if (j >= 0) do { d = vd[j]; } while ((d >> 32) == 0ull);
-                const unsigned pref = __ballot_sync(0xffffffffu, (d >> 32) == BM_FLAG_PREFIX);
-                const int first = __ffs(pref) - 1;                     // nearest predecessor with an inclusive prefix
-                int v = (pref == 0u || lane <= first) ? (int)(unsigned)d : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                base += v;
-                if (pref) break;
-            }
-        }
+        if (c > 0 && lane == 0) vd[c] = (SASSD_SCAN_AGG << 32) | (unsigned)total;
+        const int base = sassd_lookback(vd, c, lane);
         if (lane == 0) {
-            vd[c] = (BM_FLAG_PREFIX << 32) | (unsigned)(base + total);
+            vd[c] = (SASSD_SCAN_PREFIX << 32) | (unsigned)(base + total);
             s_base = base;
             if (c == nchunks - 1) {
                 int all = base + total;
@@ -249,32 +232,27 @@ bm_compact_kernel(const uint4* __restrict__ bitmap4, int nwords, unsigned long l
     }
     __syncthreads();
     const int base_row = s_base;
-    if (mine) {
+    if (m) {
         int row = base_row + ex;
-        // (b, z, y, x) of the first cell of my first word; then walk with carries (no division per row)
-        int cell0 = w0 * 32;
+        // (b, z, y, x) of the word's first cell; then walk with carries (no division per row)
+        int cell0 = w * 32;
         int x = cell0 % Wo; cell0 /= Wo;
         int y = cell0 % Ho; cell0 /= Ho;
         int z = cell0 % Do;
         int b = cell0 / Do;
         int at = 0;                                              // cells advanced since (b, z, y, x) was computed
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t m = bits[i];
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                const int tgt = i * 32 + bit;
-                x += tgt - at; at = tgt;
-                while (x >= Wo) { x -= Wo; if (++y == Ho) { y = 0; if (++z == Do) { z = 0; ++b; } } }
-                if (row < rows_cap) coors_out[row] = make_int4(b, z, y, x);
-                ++row;
-            }
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            x += bit - at; at = bit;
+            while (x >= Wo) { x -= Wo; if (++y == Ho) { y = 0; if (++z == Do) { z = 0; ++b; } } }
+            if (row < rows_cap) coors_out[row] = make_int4(b, z, y, x);
+            ++row;
         }
     }
     if (!keys) return;
     // Hash the chunk's rows with the whole CTA, one row per thread and round: an insertion is a chain of dependent L2
-    // atomics, so the thread that owns 128 consecutive cells must not do its (up to dozens of) rows one after the other.
+    // atomics, so a thread must not do the rows of its own word one after the other.
     __syncthreads();                                             // the rows above are visible to the CTA
     const uint32_t mask = (uint32_t)slots - 1u;
     const int nrows = min(total, max(rows_cap - base_row, 0));
@@ -323,7 +301,7 @@ extern "C" int sassd_rulebook_conv_outputs_hash(const int32_t* coors_in, const i
     if (keys_out) cudaMemsetAsync(keys_out, 0xff, (size_t)slots_out * sizeof(int), stream);
     conv_mark_kernel<<<sassd_grid((long long)(rows_cap_in > 0 ? rows_cap_in : 1) * 8, 256), 256, 0, stream>>>(
         (const int4*)coors_in, d_rows_in, rows_cap_in, Do, Ho, Wo, bitmap);
-    bm_compact_kernel<<<nchunks, BM_CHUNK / 4, 0, stream>>>((const uint4*)bitmap, nwords, desc, nchunks, Do, Ho, Wo, rows_cap_out,
+    bm_compact_kernel<<<nchunks, BM_CHUNK, 0, stream>>>(bitmap, nwords, desc, nchunks, Do, Ho, Wo, rows_cap_out,
                                                    (int4*)coors_out, d_rows_out, keys_out, vals_out, slots_out, d_status);
     return sassd_check_launch();
 }

@@ -461,7 +461,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
         int acc = 0;
         uint32_t acc_phase = 0;
         const int r = warp * 32 + lane;
-        const bool vec_ss = p.scale && p.shift && (p.cout & 3) == 0;
         for (int ii = 0; ii < n_items; ++ii) {
             const Item item = item_at(ii);
             const int tile = item.tile, part = item.part;
@@ -490,6 +489,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
             for (int c0 = 0; c0 < BN; c0 += CW) {
                 uint32_t v[CW], u[CW], w[CW];
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + c0);
+                const int nl = c0 + (lane & (CW - 1));
+                const float scl = (p.scale && nl < p.cout) ? __ldg(&p.scale[nl]) : 1.f;
+                const float shl = (p.shift && nl < p.cout) ? __ldg(&p.shift[nl]) : 0.f;
                 float4 q4[CW / 4];              // keeper: the peer's partial sums, requested before the TMEM loads
                 if (split && !giver) {
 #pragma unroll
@@ -528,39 +530,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS3, 1) s
                         a[j + 2] = __fadd_rn(a[j + 2], q.z); a[j + 3] = __fadd_rn(a[j + 3], q.w);
                     }
                 }
+                // folded BN: lane l holds scale / shift of column c0 + (l & 15) (loaded above, before the TMEM loads) and
+                // every lane takes them by shuffle - instead of 8 dependent float4 loads behind branches per slice
+                float o[CW];
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    float val = fmaf(a[j], __shfl_sync(0xffffffffu, scl, j), __shfl_sync(0xffffffffu, shl, j));
+                    if (p.relu) val = fmaxf(val, 0.f);
+                    o[j] = val;                  // columns >= cout: zero weights, scale 1, shift 0 -> exactly 0
+                }
                 if (m < M) {
-                    float o[CW];
-#pragma unroll
-                    for (int j = 0; j < CW; j += 4) {
-                        const int n = c0 + j;
-                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (vec_ss) {
-                            if (n < p.cout) {
-                                sc = __ldg((const float4*)(p.scale + n));
-                                sh = __ldg((const float4*)(p.shift + n));
-                            }
-                        } else {
-                            if (p.scale) {
-                                if (n + 0 < p.cout) sc.x = __ldg(&p.scale[n + 0]);
-                                if (n + 1 < p.cout) sc.y = __ldg(&p.scale[n + 1]);
-                                if (n + 2 < p.cout) sc.z = __ldg(&p.scale[n + 2]);
-                                if (n + 3 < p.cout) sc.w = __ldg(&p.scale[n + 3]);
-                            }
-                            if (p.shift) {
-                                if (n + 0 < p.cout) sh.x = __ldg(&p.shift[n + 0]);
-                                if (n + 1 < p.cout) sh.y = __ldg(&p.shift[n + 1]);
-                                if (n + 2 < p.cout) sh.z = __ldg(&p.shift[n + 2]);
-                                if (n + 3 < p.cout) sh.w = __ldg(&p.shift[n + 3]);
-                            }
-                        }
-                        const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float val = fmaf(a[j + e], scs[e], shs[e]);
-                            if (p.relu) val = fmaxf(val, 0.f);
-                            o[j + e] = (n + e) < p.cout ? val : 0.f;
-                        }
-                    }
                     if (p.out_f32) {
                         float* orow = p.out_f32 + (size_t)m * p.out_f32_stride;
 #pragma unroll

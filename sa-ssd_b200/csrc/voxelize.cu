@@ -41,10 +41,16 @@ __device__ __forceinline__ int vox_frame_of(const int* s_off, int batch, int i) 
 __global__ void __launch_bounds__(256)
 vox_insert_kernel(const float4* __restrict__ points, const int* __restrict__ pt_off, int batch, VoxConst P,
                   int slots, int* __restrict__ keys, int* __restrict__ first, int* __restrict__ head,
-                  int* __restrict__ pt_slot, int* __restrict__ pt_next, int* __restrict__ status) {
+                  int* __restrict__ pt_slot, int* __restrict__ pt_next, int* __restrict__ status,
+                  int* __restrict__ frame_m, int* __restrict__ frame_cut, unsigned long long* __restrict__ rank_desc,
+                  int n_desc) {
     __shared__ int s_off[VOX_MAX_BATCH + 1];
     for (int b = threadIdx.x; b <= batch; b += blockDim.x) s_off[b] = pt_off[b];
     __syncthreads();
+    if (blockIdx.x == 0) {          // presets for vox_rank_kernel (the next launch): no voxel, no cut, nothing published
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) { frame_m[b] = 0; frame_cut[b] = s_off[b + 1]; }
+        for (int i = threadIdx.x; i < n_desc; i += blockDim.x) rank_desc[i] = 0ull;
+    }
     const int n = s_off[batch];
     const uint32_t mask = (uint32_t)slots - 1u;
     const int lane = threadIdx.x & 31;
@@ -103,50 +109,56 @@ vox_insert_kernel(const float4* __restrict__ points, const int* __restrict__ pt_
     }
 }
 
-// One CTA per frame; ordered ranking of voxel openers.
+// Ordered ranking of voxel openers (a point opens a voxel when it is the first point of its cell): rank = number of
+// openers before it in the frame's point order - the reference's first-touch voxel order (points_ops.py:4-50).
+// Round 1: one CTA per frame, 32 points per thread in three 32x-unrolled passes - 17-24 us at the very start of every
+// step's critical path, most of it instruction fetch for code that runs once.  Now VR_CHUNK points per CTA (8
+// consecutive points per thread), the chunk totals chained by decoupled look-back (descriptors zeroed, and frame_m /
+// frame_cut preset, by vox_insert_kernel, which runs before).
+#define VR_PTS 8
+#define VR_CHUNK (1024 * VR_PTS)
 __global__ void __launch_bounds__(1024)
 vox_rank_kernel(const int* __restrict__ pt_off, const int* __restrict__ pt_slot, const int* __restrict__ first,
-                int* __restrict__ vid, int max_voxels, int* __restrict__ frame_m, int* __restrict__ frame_cut) {
+                int* __restrict__ vid, int max_voxels, int* __restrict__ frame_m, int* __restrict__ frame_cut,
+                unsigned long long* __restrict__ desc, int chunks_max) {
     __shared__ int s_scan[33];
-    __shared__ int s_cut;
-    const int b = blockIdx.x;
+    __shared__ int s_base;
+    const int b = blockIdx.y, c = blockIdx.x;
     const int beg = pt_off[b], end = pt_off[b + 1];
-    if (threadIdx.x == 0) s_cut = end;
-    __syncthreads();
-    int base = 0;
-    // rounds of 1024 threads x 32 consecutive points; thread-local bitmask keeps the flags
-    for (int r0 = beg; r0 < end; r0 += 1024 * 32) {
-        const int t0 = r0 + threadIdx.x * 32;
-        uint32_t flags = 0;
-        int slots_l[32];
+    const int nchunks = (end - beg + VR_CHUNK - 1) / VR_CHUNK;
+    if (c >= nchunks) return;
+    const int t0 = beg + c * VR_CHUNK + (int)threadIdx.x * VR_PTS;
+    uint32_t flags = 0;
+    int slots_l[VR_PTS];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int i = t0 + j;
-            slots_l[j] = (i < end) ? __ldg(&pt_slot[i]) : -1;
-        }
+    for (int j = 0; j < VR_PTS; ++j) slots_l[j] = (t0 + j < end) ? __ldg(&pt_slot[t0 + j]) : -1;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int s = slots_l[j];
-            if (s >= 0 && __ldg(&first[s]) == t0 + j) flags |= 1u << j;
+    for (int j = 0; j < VR_PTS; ++j) {
+        const int s = slots_l[j];
+        if (s >= 0 && __ldg(&first[s]) == t0 + j) flags |= 1u << j;
+    }
+    int total;
+    const int ex = sassd_block_exscan(__popc(flags), s_scan, &total);
+    if (threadIdx.x < 32) {
+        volatile unsigned long long* vd = desc + (size_t)b * chunks_max;
+        const int lane = threadIdx.x;
+        if (c > 0 && lane == 0) vd[c] = (SASSD_SCAN_AGG << 32) | (unsigned)total;
+        const int base = sassd_lookback(vd, c, lane);
+        if (lane == 0) {
+            vd[c] = (SASSD_SCAN_PREFIX << 32) | (unsigned)(base + total);
+            s_base = base;
+            if (c == nchunks - 1) frame_m[b] = min(base + total, max_voxels);
         }
-        int total;
-        int ex = sassd_block_exscan(__popc(flags), s_scan, &total);
-        int rank = base + ex;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (flags & (1u << j)) {
-                vid[slots_l[j]] = rank < max_voxels ? rank : -1;
-                if (rank == max_voxels) s_cut = t0 + j;
-                ++rank;
-            }
-        }
-        base += total;
-        if (base > max_voxels) break;  // uniform: every later opener is past the cut
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        frame_m[b] = base < max_voxels ? base : max_voxels;
-        frame_cut[b] = s_cut;
+    int rank = s_base + ex;
+#pragma unroll
+    for (int j = 0; j < VR_PTS; ++j) {
+        if (flags & (1u << j)) {
+            vid[slots_l[j]] = rank < max_voxels ? rank : -1;
+            if (rank == max_voxels) frame_cut[b] = t0 + j;       // the first opener past the cut (exactly one writer)
+            ++rank;
+        }
     }
 }
 
@@ -237,7 +249,9 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t sassd_voxelize_workspace_bytes(int n_points_cap, int batch, int slots_per_frame) {
     size_t t = (size_t)batch * slots_per_frame * sizeof(int);
-    return 4 * align256(t) + 2 * align256((size_t)n_points_cap * sizeof(int)) + 2 * align256((size_t)batch * sizeof(int));
+    const size_t chunks_max = ((size_t)(n_points_cap > 0 ? n_points_cap : 1) + VR_CHUNK - 1) / VR_CHUNK;
+    return 4 * align256(t) + 2 * align256((size_t)n_points_cap * sizeof(int)) + 2 * align256((size_t)batch * sizeof(int)) +
+           align256((size_t)batch * chunks_max * sizeof(unsigned long long));
 }
 
 extern "C" int sassd_voxelize(const float* points, const int32_t* d_pt_off, int n_points_cap, int batch,
@@ -263,7 +277,9 @@ extern "C" int sassd_voxelize(const float* points, const int32_t* d_pt_off, int 
     int* pt_slot = (int*)w; w += pn;
     int* pt_next = (int*)w; w += pn;
     int* frame_m = (int*)w; w += align256((size_t)batch * sizeof(int));
-    int* frame_cut = (int*)w;
+    int* frame_cut = (int*)w; w += align256((size_t)batch * sizeof(int));
+    unsigned long long* rank_desc = (unsigned long long*)w;
+    const int chunks_max = (n_points_cap + VR_CHUNK - 1) / VR_CHUNK;
 
     VoxConst P;
     for (int j = 0; j < 3; ++j) { P.vs[j] = hp->voxel_size[j]; P.lo[j] = hp->range_min[j]; P.grid[j] = hp->grid[j]; }
@@ -274,8 +290,10 @@ extern "C" int sassd_voxelize(const float* points, const int32_t* d_pt_off, int 
     cudaMemsetAsync(head, 0xff, t, stream);   // -1
     const int grid = sassd_grid(n_points_cap, 256);
     vox_insert_kernel<<<grid, 256, 0, stream>>>((const float4*)points, d_pt_off, batch, P, slots_per_frame, keys,
-                                                first, head, pt_slot, pt_next, d_status);
-    vox_rank_kernel<<<batch, 1024, 0, stream>>>(d_pt_off, pt_slot, first, vid, P.max_voxels, frame_m, frame_cut);
+                                                first, head, pt_slot, pt_next, d_status, frame_m, frame_cut, rank_desc,
+                                                batch * chunks_max);
+    vox_rank_kernel<<<dim3(chunks_max, batch), 1024, 0, stream>>>(d_pt_off, pt_slot, first, vid, P.max_voxels, frame_m,
+                                                                   frame_cut, rank_desc, chunks_max);
     vox_offsets_kernel<<<1, 32, 0, stream>>>(frame_m, batch, rows_cap, d_frame_rows, d_status);
     vox_emit_kernel<<<grid, 256, 0, stream>>>((const float4*)points, d_pt_off, batch, P, pt_slot, pt_next, first,
                                               head, vid, frame_cut, d_frame_rows, rows_cap, (float4*)voxels,

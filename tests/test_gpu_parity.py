@@ -176,6 +176,18 @@ def test_rulebooks_bit_exact(dev, case):
     op, on = O.nbr_to_indice_pairs(onbr, n_cap=cap)
     assert np.array_equal(num.cpu().numpy(), on)
     assert np.array_equal(pairs.cpu().numpy(), op)
+    # the fused form (the product path): the compaction pass hashes the output level as it writes the rows; the SubM
+    # table of that level built on this hash must equal the oracle's (and the one built on a separate hash_build)
+    idx_out = ops.HashIndex(cap, dev)
+    co2, dn2, so2 = ops.rulebook_conv_outputs(x._indices, x.d_rows, B, shape, cap, x.status, ws_key="t_fused",
+                                              index_out=idx_out)
+    assert int(dn2.item()) == n and so2 == oshape and np.array_equal(co2[:n].cpu().numpy(), oc)
+    nbr_next, _ = ops.rulebook_subm(co2, dn2, so2, idx_out)
+    assert np.array_equal(nbr_next[:n].cpu().numpy(), O.subm_rulebook(oc, oshape))
+    idx_sep = ops.hash_build(ops.HashIndex(cap, dev), co, dn, B, so, x.status)
+    nbr_sep, _ = ops.rulebook_subm(co, dn, so, idx_sep)
+    assert np.array_equal(nbr_next[:n].cpu().numpy(), nbr_sep[:n].cpu().numpy())
+    x.check_status()
 
 
 def test_rulebook_capacity_overflow_is_flagged(dev):
