@@ -470,7 +470,8 @@ def run_ours(args, rank, world, local):
     finally:
         _ops.CONV2D_TILE_ORDER = order0
     tiles_map = B * 25 * 11
-    nsplit_on = graph is not None and tiles_map <= _ops.CONV2D_NSPLIT_MAX_TILES and args.precision == "f16x3"
+    nsplit_on = args.precision == "f16x3" and tiles_map <= (_ops.CONV2D_NSPLIT_MAX_TILES if graph is not None else
+                                                             _ops.CONV2D_NSPLIT_MAX_TILES_STREAM)
     peaks = load_peaks()
     H, W = 200, 176
     dom = max(prof.items(), key=lambda kv: kv[1]["ms_total_per_step"])

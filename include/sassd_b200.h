@@ -51,6 +51,11 @@ enum { /* bits of *d_status */
 };
 
 int sassd_version(void);
+/* Launch hint, process-wide: on != 0 launches the tensor-core conv kernels as programmatic dependents of their
+ * predecessors (their prologues overlap the previous layer's tail); -1 restores the default (environment SASSD_PDL,
+ * else off).  Worth ~2 % for a step that runs alone on the GPU, costs throughput when several steps are in flight, so set
+ * it around the capture of a latency-oriented graph only.  Returns the previous setting.  Results never change. */
+int sassd_set_pdl(int on);
 
 /* ------------------------------------------------------------------------
  * Voxelization.  Replaces mmdet/ops/points_op/points_ops.py:104-164

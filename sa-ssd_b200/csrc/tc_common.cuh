@@ -301,11 +301,15 @@ __device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi2, uin
     lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// Host: launch `kern`, optionally (SASSD_PDL=1) as a programmatic dependent of the previous kernel in the stream.
-// Every kernel launched through here calls pdl_wait() before touching global data.  Off by default: measured
-// +0.9 % with one step on the GPU at a time, but -4.5 % with four captured steps in flight, where the early-resident
-// CTAs of the next layer sit on SMs that another frame's kernels could have used.
+// Host: launch `kern`, optionally as a programmatic dependent of the previous kernel in the stream (every kernel launched
+// through here calls pdl_wait() before touching global data, so only its prologue overlaps the predecessor's tail).
+// Measured (round 2, B=1): +2 % with one step on the GPU at a time, -8 % with four captured steps in flight, where the
+// early-resident CTAs of the next layer sit on SMs another frame's kernels could have used.  So it is a per-capture
+// choice: sassd_set_pdl(1) while the latency graph is captured (detectors._GraphedStep), off otherwise; the environment
+// variable SASSD_PDL=0/1 is the default when sassd_set_pdl was never called (experiments).
+extern int g_sassd_pdl;      // -1: not set (voxelize.cu)
 inline bool pdl_enabled() {
+    if (g_sassd_pdl >= 0) return g_sassd_pdl != 0;
     static const bool on = [] { const char* e = getenv("SASSD_PDL"); return e && atoi(e) != 0; }();
     return on;
 }

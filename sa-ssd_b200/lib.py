@@ -54,6 +54,7 @@ _SIGNATURES = {
     "sassd_rulebook_subm": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
     "sassd_rulebook_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sassd_rulebook_conv_outputs": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, c_size_t, P]),
+    "sassd_set_pdl": (c_int, [c_int]),
     "sassd_rulebook_conv_outputs_hash": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, c_int, P, P,
                                                  c_size_t, P]),
     "sassd_rulebook_conv_nbr": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P]),
