@@ -33,6 +33,23 @@ def test_argument_validation_without_gpu():
     with pytest.raises(L.SassdError):
         L.check(-3, "x")
     assert L.decode_flags(2 | 8) == ["ROWS_CAP", "NMS_CAP"]
+    # round-2 entry points
+    assert lib.sassd_rulebook_conv_outputs_hash(None, None, 0, 1, 40, 1600, 1408, None, None, 0, None, None, 0, None,
+                                                None, 0, None) == -1
+    one = ctypes.c_void_p(8)            # never dereferenced on these paths: the argument checks come first
+    assert lib.sassd_rulebook_conv_outputs_hash(one, one, 4, 1, 8, 16, 16, one, one, 10, one, one, 12, one, one, 1 << 20,
+                                                None) == -1          # slots_out not a power of two >= 2 * rows_cap_out
+    d = L.Conv2dDesc()
+    d.batch, d.H, d.W, d.cin, d.cin_stored, d.cout, d.taps, d.relu = 1, 200, 176, 256, 256, 256, 9, 1
+    # constant-region rule outside its validity range: reach beyond the recorded tile distances
+    assert lib.sassd_conv2d_f16x3_occ(ctypes.byref(d), one, one, None, None, None, one, one, 10, one, None, None) == \
+        -4
+    d.H = 201                           # a 1-pixel partial edge tile cannot absorb a 3-pixel padding disturbance
+    assert lib.sassd_conv2d_f16x3_occ(ctypes.byref(d), one, one, None, None, None, one, one, 4, one, None, None) == \
+        -4
+    # launch hint: returns the previous setting
+    prev = lib.sassd_set_pdl(1)
+    assert lib.sassd_set_pdl(prev) == 1
 
 
 def test_product_never_imports_the_oracle():
